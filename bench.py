@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the fused J/K Fock build (BASELINE.json metric) -- one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nbf 494]
+
+Workload: one RHF Fock build (J and K, hf_ksdft.py:483-495) over the synthetic 8-fold packed ERI tensor of
+the anthracene-size configuration (N = 494 basis functions, 59.8 GB packed, BASELINE.json configs[4] --
+the configuration the north_star target is quoted on; it fits one B200).  At N GPUs the SAME tensor is
+sharded by pair-block rows over the ranks (strong scaling): each rank streams its shard once, the
+partial [J; K] is summed with one NCCL all-reduce.  A "step" is one Fock build.
+
+  value        builds/s, density and outputs resident in HBM (device pointers), CUDA-event timed, max over ranks
+  e2e          builds/s through the host-buffer API (numpy D in, numpy J/K out; H2D + D2H inside the timed region)
+  roofline     dominant kernel (jk_tiled_kernel): algorithmic bytes 8*nquad(shard) / CUDA-event kernel time
+  cpu_baseline the oracle's multi-core C port of the same pass, timed on a bounded row sample of the same tensor
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20261019
+NOCC = {62: 7, 222: 21, 264: 21, 494: 47}
+
+
+def nquad(n):
+    p = n * (n + 1) // 2
+    return p * (p + 1) // 2
+
+
+def density_rhf(n, n_occ, seed):
+    """D = 2 C_occ C_occ^T from a seeded orthonormal C (same recipe as oracle/synth.py)."""
+    q, _ = np.linalg.qr(np.random.default_rng(seed).standard_normal((n, n)))
+    return 2.0 * q[:, :n_occ] @ q[:, :n_occ].T
+
+
+def density_uhf(n, n_a, n_b, seed):
+    qa, _ = np.linalg.qr(np.random.default_rng(seed).standard_normal((n, n)))
+    qb, _ = np.linalg.qr(np.random.default_rng(seed + 1).standard_normal((n, n)))
+    return np.stack([qa[:, :n_a] @ qa[:, :n_a].T, qb[:, :n_b] @ qb[:, :n_b].T])
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nbf", type=int, default=494, help="basis functions of the synthetic packed ERI")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary (N=222/264, UHF, LDA, MP2) measurements")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = get(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def cpu_port_baseline(n, d, seconds):
+    """Multi-core C port (oracle) of the one-pass 8-fold J/K accumulation on a bounded sample of rows of the SAME
+    synthetic tensor: the last rows (longest) that fit ~1.5 GB; builds/s = sample elements/s / nquad."""
+    from oracle import cjk
+    npair = n * (n + 1) // 2
+    budget = int(1.5e9 // 8)
+    ij0 = npair
+    while ij0 > 0 and npair * (npair + 1) // 2 - (ij0 - 1) * ij0 // 2 <= budget:
+        ij0 -= 1
+    # coarse: shrink the sample further so one pass takes at most ~seconds/3
+    rows = cjk.synth_rows(n, SEED, ij0, npair)
+    elems = rows.size
+    cjk.jk_packed_rows(rows, n, ij0, npair, d)  # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        cjk.jk_packed_rows(rows, n, ij0, npair, d)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el > seconds or reps >= 50:
+            break
+    per_elem = el / (reps * elems)
+    builds = 1.0 / (per_elem * nquad(n))
+    return {"value": builds, "unit": "builds/s", "cores": cjk.num_threads(), "kind": "port",
+            "sample": f"rows ij in [{ij0},{npair}) of the N={n} synthetic packed tensor ({elems * 8 / 1e9:.2f} GB, "
+                      f"{reps} passes, {el:.1f} s), oracle/csrc/jk_oracle.c one-pass 8-fold J/K with OpenMP; "
+                      f"extrapolated by element count to the whole tensor",
+            "gbs": 8.0 / per_elem / 1e9}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU form of the path (hf_ksdft.py:483-495: per (p,q) an elementwise
+    multiply + np.sum over an N x N slab, J then K), numpy, on a bounded sample of (p,q) entries per step."""
+    from oracle import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.nbf
+    d = synth.synth_density_rhf(n, NOCC.get(n, max(1, n // 10)), 7)
+    rng = np.random.default_rng(1)
+    m = 24  # sampled (p, q) entries per step
+    pq = [(int(a), int(b)) for a, b in rng.integers(0, n, size=(m, 2))]
+    slabs_j = [synth.synth_eri_slab_pq(n, SEED, p, q) for p, q in pq]      # ERI[p,q,:,:]
+    slabs_k = [synth.synth_eri_slab_pxqx(n, SEED, p, q) for p, q in pq]    # ERI[p,:,q,:] (contiguous copy)
+
+    def step():
+        acc = 0.0
+        for sj, sk in zip(slabs_j, slabs_k):
+            acc += np.sum(sj * d)      # hf_ksdft.py:486-487
+            acc += np.sum(sk * d)      # hf_ksdft.py:494-495
+        return acc
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    per_entry = el / (args.steps * m)
+    ms_per_build = per_entry * n * n * 1e3
+    value = 1e3 / ms_per_build
+    sample = (f"{m} random (p,q) entries per step of the N={n} synthetic tensor (slabs pre-generated outside the timed "
+              f"region); one build = N^2 = {n * n} entries, extrapolated")
+    line = {"impl": "reference", "metric": "J/K Fock builds/sec", "value": value, "unit": "builds/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_build,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"RHF J+K Fock build, synthetic 8-fold symmetric ERI, N={n} basis functions",
+                       "nbf": n, "nquad": nquad(n)},
+            "cpu_baseline": {"value": value, "unit": "builds/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "builds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from sqcc_b200.backend import FockEngine   # the product path; oracle/ is only used by the CPU-baseline legs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.nbf
+    eng = FockEngine(device=local, rank=rank, world=world)
+    eng.attach_eri_synth(n, SEED)
+    eng.synchronize()
+    d_host = density_rhf(n, NOCC.get(n, max(1, n // 10)), 7)
+    d_dev = torch.from_numpy(d_host).to(eng.device)
+    out = torch.empty((2, n, n), dtype=torch.float64, device=eng.device)
+    native_bytes, algo_bytes = eng.eri_bytes()
+    peak, peak_src = peaks()
+
+    # ---- device-resident throughput (value)
+    for _ in range(args.warmup):
+        eng.jk_device(d_dev, True, out)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.jk_device(d_dev, True, out)
+    e1.record()
+    barrier()
+    clocks = sampler.result()
+    launches = eng.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+
+    # ---- dominant-kernel time, per launch, CUDA events on the launching stream (roofline)
+    ktimes = []
+    for _ in range(max(3, min(args.steps, 10))):
+        eng.jk_device(d_dev, True, out)
+        ktimes.append(eng.timings()["jk_kernel"])
+    k_ms = float(np.mean(ktimes))
+    kt = torch.tensor([k_ms], dtype=torch.float64, device=eng.device)
+    ab = torch.tensor([float(algo_bytes)], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    achieved = float(ab.item()) / (float(kt.item()) * 1e-3) / 1e9  # GB/s on the slowest rank's shard
+
+    # ---- end to end through host buffers
+    for _ in range(max(1, args.warmup // 2)):
+        eng.jk(d_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        j_h, k_h = eng.jk(d_host)
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_builds = args.steps / float(t_e2e.item())
+
+    if rank == 0:
+        line = {
+            "metric": "J/K Fock builds/sec", "value": 1e3 / ms_per_step, "unit": "builds/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"RHF J+K Fock build, synthetic 8-fold packed ERI, N={n} basis functions "
+                                   f"(anthracene def2-TZVP size), pair-block sharded over {world} GPU(s)",
+                       "nbf": n, "nquad": nquad(n), "packed_gb_algorithmic": nquad(n) * 8 / 1e9,
+                       "native_gb_rank0": native_bytes / 1e9, "parallelism": f"pair-block shard x{world} + all-reduce",
+                       "l2_policy": "inputs larger than L2 (ERI shard >> 126 MB streamed every step)"},
+            "eri_gbs_aggregate": nquad(n) * 8 / (ms_per_step * 1e-3) / 1e9,
+            "frac_of_8tbs_per_gpu": nquad(n) * 8 / (ms_per_step * 1e-3) / 1e9 / world / 8000.0,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "jk_tiled_kernel", "kernel_ms": float(kt.item()),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": float(ab.item())},
+            "e2e": {"value": e2e_builds, "unit": "builds/s", "h2d_bytes_per_step": int(d_host.nbytes),
+                    "d2h_bytes_per_step": int(2 * n * n * 8)},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1:
+            line["cpu_baseline"] = cpu_port_baseline(n, d_host, args.cpu_seconds)
+        if world == 1 and not args.no_extras:
+            try:
+                line["extras"] = extras(eng, torch)
+            except Exception as exc:  # extras never invalidate the headline line
+                line["extras"] = {"error": repr(exc)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extras(eng, torch):
+    """Secondary measurements at 1 GPU (CUDA-event kernel times): other basis sizes, UHF, J-only."""
+    res = {}
+    for n in (264, 222):
+        eng.attach_eri_synth(n, SEED)
+        _, ab = eng.eri_bytes()
+        for tag, d, wk in (("rhf", density_rhf(n, NOCC[n], 7), True),
+                           ("uhf", density_uhf(n, NOCC[n] + 1, NOCC[n] - 1, 7), True),
+                           ("j_only", density_rhf(n, NOCC[n], 7), False)):
+            dd = torch.from_numpy(d).to(eng.device)
+            ts = []
+            for it in range(8):
+                eng.jk_device(dd, wk)
+                if it >= 3:
+                    ts.append(eng.timings()["jk_kernel"])
+            t = float(np.mean(ts))
+            res[f"n{n}_{tag}"] = {"kernel_ms": t, "gbs": ab / (t * 1e-3) / 1e9, "builds_per_s_kernel": 1e3 / t}
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,125 @@
+/* sqcc_b200.h -- C ABI of libsqcc_b200.so: the B200-native SCF Fock-build hot path of SQCC.
+ *
+ * The reference (QuantumChemistrySchoolJapan-HFT/sqcc) has NO plugin / FFI seam for this path: the
+ * contractions are Python loop nests inlined in hf_ksdft.Calculator.scf() and mp2.Calculator.mp2().
+ * Each entry point below therefore cites the reference loop nest it replaces (file:line under
+ * /root/reference/code/python3).  INTEGRATION.md shows the ctypes binding a maintainer of the reference
+ * would add at those lines.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative sqcc_status on error; sqcc_last_error() returns
+ *     a thread-local message.  No exceptions cross the ABI.
+ *   - one sqcc_ctx drives ONE device (one process per GPU; cross-rank sums are done by the caller with
+ *     torch.distributed/NCCL on the output buffers).  A context is not thread-safe.
+ *   - "d_" pointers are device pointers owned by the CALLER (e.g. torch tensors' data_ptr()); the
+ *     library never frees them.  "h_" pointers are host pointers.  Scratch lives in the context.
+ *   - all matrices are row-major float64.  D / J / K / Vxc are dense [N,N] (or [nspin,N,N]).
+ *   - work is enqueued on the context's stream (sqcc_ctx_set_stream; default: the legacy stream 0).
+ *     Functions with "_host" in the name synchronise that stream before returning.
+ *
+ * Packed ERI layouts (8-fold symmetry, i>=j, k>=l, ij>=kl, ij = i(i+1)/2+j):
+ *   canonical : offset ij(ij+1)/2 + kl, plain (ij|kl).
+ *   native v1 : same row order; inside row ij the sub-row of k (l = 0..k, or 0..j when k == i) is
+ *               padded to an even length (16-byte aligned sub-rows, zero pad cells); the stored value
+ *               is (ij|kl) * 0.5^[i==j] * 0.5^[k==l] * 0.5^[ij==kl].  A rank holds the contiguous
+ *               row range [ij_begin, ij_end) ("pair-block shard").
+ */
+#ifndef SQCC_B200_H
+#define SQCC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sqcc_ctx sqcc_ctx;
+
+typedef enum {
+    SQCC_OK = 0,
+    SQCC_ERR_INVALID = -1,   /* bad argument / state */
+    SQCC_ERR_CUDA = -2,      /* CUDA runtime error (message in sqcc_last_error) */
+    SQCC_ERR_NOMEM = -3,
+    SQCC_ERR_UNSUPPORTED = -4
+} sqcc_status;
+
+/* ---- library / context --------------------------------------------------------------------- */
+int sqcc_version(void);
+const char *sqcc_last_error(void);
+int sqcc_device_count(int *count);
+int sqcc_ctx_create(int device, sqcc_ctx **out);
+int sqcc_ctx_destroy(sqcc_ctx *ctx);
+int sqcc_ctx_set_stream(sqcc_ctx *ctx, void *cuda_stream);
+int sqcc_ctx_synchronize(sqcc_ctx *ctx);
+
+/* ---- layout helpers (pure host arithmetic, usable without a GPU) --------------------------- */
+int64_t sqcc_npair(int n);
+int64_t sqcc_nquad(int n);
+/* Equal-area cut of the row range into `world` contiguous pair-block shards; cuts fall
+ * on rows (i,0) with i a multiple of 4 so kernels can tile rows by i-block. */
+int sqcc_shard_rows(int n, int world, int rank, int64_t *ij_begin, int64_t *ij_end);
+/* Length in doubles of the native-v1 shard holding rows [ij_begin, ij_end). */
+int64_t sqcc_native_len(int n, int64_t ij_begin, int64_t ij_end);
+/* Offset (doubles, relative to the shard start) of element (i,j,k,l) in native v1; -1 if not canonical. */
+int64_t sqcc_native_offset(int n, int64_t ij_begin, int i, int j, int k, int l);
+
+/* ---- ERI ingest: replaces the consumption of interface_psi4.py:177-190 (full N^4 host tensor) ---- */
+/* Attach a caller-owned device buffer of sqcc_native_len(...) doubles as this rank's ERI shard and build
+ * the tile schedule.  The buffer must stay alive until detach/destroy. */
+int sqcc_eri_attach(sqcc_ctx *ctx, double *d_native, int n, int64_t ij_begin, int64_t ij_end);
+/* Fill the attached shard with the counter-based synthetic tensor (oracle/synth.py). */
+int sqcc_eri_synth(sqcc_ctx *ctx, uint64_t seed);
+/* Pack a slab ERI[p0:p0+np, :, :, :] of the full tensor (device pointer, [np,N,N,N]) into the shard. */
+int sqcc_eri_pack_full_slab(sqcc_ctx *ctx, const double *d_slab, int p0, int np);
+/* Same, from a pageable/pinned HOST tensor ERI[N,N,N,N]; streams slabs through a pinned staging buffer. */
+int sqcc_eri_pack_full_host(sqcc_ctx *ctx, const double *h_eri_full);
+/* Pack canonical packed rows [ij0, ij0+nrows) (device pointer to the first element of row ij0). */
+int sqcc_eri_pack_canonical(sqcc_ctx *ctx, const double *d_rows, int64_t ij0, int64_t nrows);
+/* Expand the attached (unsharded) ERI into the full [N,N,N,N] device tensor (plain values). */
+int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full);
+
+/* ---- fused Coulomb/exchange build: replaces hf_ksdft.py:483-495 (RHF/RKS) and :510-535 (UHF/UKS) ----
+ * nspin = 1: J = J(D), K = K(D);  nspin = 2: J = J(D[0]+D[1]), K[s] = K(D[s]).
+ * want_k = 0 skips exchange (KS-DFT, hf_ksdft.py:488/:517).  One pass over this rank's ERI shard; the
+ * outputs are this rank's PARTIAL (already symmetrised) J/K -- sum over ranks gives the full matrices. */
+int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_J, double *d_K);
+/* Same through host buffers (H2D of D, D2H of J/K inside; stream-synchronous). */
+int sqcc_jk_build_host(sqcc_ctx *ctx, const double *h_D, int nspin, int want_k, double *h_J, double *h_K);
+/* Select the kernel: 0 = tiled register kernel (default), 1 = simple atomics kernel (cross-check). */
+int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant);
+
+/* ---- LDA exchange grid quadrature: replaces hf_ksdft.py:426-440, :634-646 (rho), ksdft_functional.py
+ * :41-65, :68-95, :98-134, :137-177 (v_x, E_x) and hf_ksdft.py:456-461, :469-476 (V_xc) ---- */
+int sqcc_grid_attach(sqcc_ctx *ctx, const double *d_phi /*[G,N]*/, const double *d_w /*[G]*/, int64_t G, int n);
+/* Vxc [nspin,N,N], Exc [1], rho [nspin,G] (optional, may be NULL); all device pointers. */
+int sqcc_lda_vxc(sqcc_ctx *ctx, const double *d_D, int nspin, double *d_Vxc, double *d_Exc, double *d_rho);
+int sqcc_lda_vxc_host(sqcc_ctx *ctx, const double *h_D, int nspin, double *h_Vxc, double *h_Exc, double *h_rho);
+/* Generic quadrature V_pq = sum_n phi_np (w_n v_n) phi_nq for a caller-supplied v (QM/MM external
+ * potential, interface_psi4.py:399-403) and rho on the attached points for a given D. */
+int sqcc_grid_quadrature(sqcc_ctx *ctx, const double *d_v /*[G]*/, double *d_V /*[N,N]*/);
+int sqcc_grid_rho(sqcc_ctx *ctx, const double *d_D /*[N,N]*/, double *d_rho /*[G]*/);
+
+/* ---- MP2: replaces mp2.py:89-99 (denominators), :123-170 (quarter transforms), :240-254 (energy) ----
+ * C is [N,N] AO x MO (columns = MOs, first n_occ occupied), eps [N].  Needs an unsharded ERI attached.
+ * d_iajb (optional) receives (ia|jb) as [n_occ,n_virt,n_occ,n_virt]. */
+int sqcc_mp2(sqcc_ctx *ctx, const double *d_C, const double *d_eps, int n_occ, double *d_ecorr, double *d_iajb);
+int sqcc_mp2_host(sqcc_ctx *ctx, const double *h_C, const double *h_eps, int n_occ, double *h_ecorr,
+                  double *h_iajb);
+/* Generic AO->MO transform (pq|rs) -> (ab|cd) with four coefficient blocks [N,n1..n4] (CIS needs (ij|ab),
+ * cis_tdhf_tda_tddft.py:128-211).  Output [n1,n2,n3,n4]. */
+int sqcc_ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2, const double *d_C3, int n3,
+               const double *d_C4, int n4, double *d_out);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+/* CUDA-event duration (ms) of the last call's dominant kernel(s): slot 0 = J/K kernel, 1 = J/K finalize,
+ * 2 = rho, 3 = vxc, 4 = mp2 transforms, 5 = mp2 energy.  Returns the number of slots written. */
+int sqcc_get_timings(sqcc_ctx *ctx, double *ms, int n);
+/* Number of library kernels launched since context creation. */
+int64_t sqcc_launch_count(sqcc_ctx *ctx);
+/* Bytes of the attached native shard (actual) and of its unique integrals (algorithmic, 8 per integral). */
+int sqcc_eri_bytes(sqcc_ctx *ctx, int64_t *native_bytes, int64_t *algorithmic_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQCC_B200_H */

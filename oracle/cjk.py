@@ -31,6 +31,9 @@ def lib():
         _lib.sqcc_oracle_jk_entries.argtypes = [ctypes.c_int, _dp, ctypes.c_int64, ctypes.c_uint64, _dp,
                                                 ctypes.c_int, _ip, ctypes.c_int64, _dp, _dp]
         _lib.sqcc_oracle_jk_packed.argtypes = [_dp, ctypes.c_int64, _dp, ctypes.c_int, ctypes.c_int, _dp, _dp]
+        _lib.sqcc_oracle_synth_rows.argtypes = [ctypes.c_int64, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, _dp]
+        _lib.sqcc_oracle_jk_packed_rows.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp,
+                                                    ctypes.c_int, ctypes.c_int, _dp, _dp]
     return _lib
 
 
@@ -83,6 +86,25 @@ def jk_packed(packed, n, d, want_k=True):
     j = np.zeros((n, n))
     k = np.zeros((nspin, n, n)) if want_k else None
     lib().sqcc_oracle_jk_packed(_p(np.ascontiguousarray(packed)), n, _p(d3), nspin, int(want_k), _p(j), _p(k))
+    if want_k and d.ndim == 2:
+        k = k[0]
+    return j, k
+
+
+def synth_rows(n, seed, ij0, ij1):
+    """Canonical packed rows [ij0, ij1) of the synthetic tensor, back to back."""
+    out = np.empty(ij1 * (ij1 + 1) // 2 - ij0 * (ij0 + 1) // 2)
+    lib().sqcc_oracle_synth_rows(n, seed, ij0, ij1, _p(out))
+    return out
+
+
+def jk_packed_rows(rows, n, ij0, ij1, d, want_k=True):
+    """Partial (symmetrised) J/K contributed by packed rows [ij0, ij1) -- what one pair-block shard computes."""
+    d3 = np.ascontiguousarray(d if d.ndim == 3 else d[None], dtype=np.float64)
+    nspin = d3.shape[0]
+    j = np.zeros((n, n))
+    k = np.zeros((nspin, n, n)) if want_k else None
+    lib().sqcc_oracle_jk_packed_rows(_p(np.ascontiguousarray(rows)), n, ij0, ij1, _p(d3), nspin, int(want_k), _p(j), _p(k))
     if want_k and d.ndim == 2:
         k = k[0]
     return j, k

@@ -81,6 +81,25 @@ void sqcc_oracle_synth_canonical(int64_t n, uint64_t seed, double *out)
     (void)np_;
 }
 
+
+/* Rows [ij0, ij1) of the synthetic canonical packed tensor, stored back to back (row ij at out + off(ij) - off(ij0)). */
+void sqcc_oracle_synth_rows(int64_t n, uint64_t seed, int64_t ij0, int64_t ij1, double *out)
+{
+    int64_t base = ij0 * (ij0 + 1) / 2;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t ij = ij0; ij < ij1; ++ij) {
+        int64_t i = (int64_t)((sqrt(8.0 * (double)ij + 1.0) - 1.0) / 2.0);
+        while (i * (i + 1) / 2 > ij) --i;
+        while ((i + 1) * (i + 2) / 2 <= ij) ++i;
+        int64_t j = ij - i * (i + 1) / 2;
+        double *row = out + (ij * (ij + 1) / 2 - base);
+        for (int64_t k = 0; k <= i; ++k) {
+            int64_t lmax = k < i ? k : j;
+            for (int64_t l = 0; l <= lmax; ++l) row[k * (k + 1) / 2 + l] = synth_value(n, seed, i, j, k, l);
+        }
+    }
+}
+
 /* source: 0 = full tensor, 1 = canonical packed, 2 = synthetic(seed) */
 static inline double eri_at(int src, const double *buf, int64_t n, uint64_t seed, int64_t a, int64_t b, int64_t c,
                             int64_t d)
@@ -123,8 +142,18 @@ void sqcc_oracle_jk_entries(int src, const double *buf, int64_t n, uint64_t seed
 /* Whole-matrix J/K from the canonical packed vector using the 8-fold accumulation of SURVEY.md A.1
  * (one pass over the packed vector, per-thread private J~/K~ then reduced).  This is the multi-core
  * "port" used as bench.py's cpu_baseline: same algorithm as the CUDA kernel, on the host cores. */
+void sqcc_oracle_jk_packed_rows(const double *packed, int64_t n, int64_t ij0, int64_t ij1, const double *D, int nspin,
+                                int want_k, double *J, double *K);
+
 void sqcc_oracle_jk_packed(const double *packed, int64_t n, const double *D, int nspin, int want_k, double *J,
                            double *K)
+{
+    sqcc_oracle_jk_packed_rows(packed, n, 0, n * (n + 1) / 2, D, nspin, want_k, J, K);
+}
+
+/* Partial J/K from rows [ij0, ij1) only; `packed` points at the first element of row ij0. */
+void sqcc_oracle_jk_packed_rows(const double *packed, int64_t n, int64_t ij0, int64_t ij1, const double *D, int nspin,
+                                int want_k, double *J, double *K)
 {
     int64_t nn = n * n;
     int nt = sqcc_oracle_num_threads();
@@ -141,13 +170,13 @@ void sqcc_oracle_jk_packed(const double *packed, int64_t n, const double *D, int
         double *jt = acc + (size_t)tid * (1 + nspin) * nn;
         double *kt0 = jt + nn, *kt1 = jt + 2 * nn;
 #pragma omp for schedule(dynamic, 8)
-        for (int64_t ijr = 0; ijr < n * (n + 1) / 2; ++ijr) {
-            int64_t ij = n * (n + 1) / 2 - 1 - ijr; /* long rows first */
+        for (int64_t ijr = 0; ijr < ij1 - ij0; ++ijr) {
+            int64_t ij = ij1 - 1 - ijr; /* long rows first */
             int64_t i = (int64_t)((sqrt(8.0 * (double)ij + 1.0) - 1.0) / 2.0);
             while (i * (i + 1) / 2 > ij) --i;
             while ((i + 1) * (i + 2) / 2 <= ij) ++i;
             int64_t j = ij - i * (i + 1) / 2;
-            const double *row = packed + ij * (ij + 1) / 2;
+            const double *row = packed + (ij * (ij + 1) / 2 - ij0 * (ij0 + 1) / 2);
             double fij = i == j ? 0.5 : 1.0;
             double dij2 = dtot[i * n + j] + dtot[j * n + i];
             double jrow = 0.0;

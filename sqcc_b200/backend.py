@@ -1,0 +1,254 @@
+"""Host-side engine over libsqcc_b200.so: device buffers (torch), pair-block sharding, NCCL all-reduce.
+
+One process drives one GPU.  With ``world > 1`` (torchrun) every rank holds the contiguous pair-block
+shard ``[ij_begin, ij_end)`` of the packed ERI tensor, builds partial J/K with one pass over its shard,
+and the partial matrices are summed with ONE ``all_reduce`` on the stacked ``[J; K]`` buffer
+(SURVEY.md 8e).  PyTorch is used only for device memory, streams and ``torch.distributed``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class ShardPlan:
+    """Equal-area cut of the packed rows over `world` ranks (pure host arithmetic, no GPU needed)."""
+
+    def __init__(self, n, world=1, rank=0):
+        lib = _lib.load()
+        self.n, self.world, self.rank = int(n), int(world), int(rank)
+        b, e = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(lib.sqcc_shard_rows(self.n, self.world, self.rank, ctypes.byref(b), ctypes.byref(e)))
+        self.ij_begin, self.ij_end = b.value, e.value
+        self.native_len = lib.sqcc_native_len(self.n, self.ij_begin, self.ij_end)
+        if self.native_len < 0:
+            raise _lib.SqccError("invalid shard")
+        # first / one-past-last i of rows (i, *) held by this rank
+        self.i_begin = int((np.sqrt(8.0 * self.ij_begin + 1.0) - 1.0) / 2.0 + 0.5)
+        self.i_end = int((np.sqrt(8.0 * self.ij_end + 1.0) - 1.0) / 2.0 + 0.5)
+
+    @staticmethod
+    def all_cuts(n, world):
+        return [ShardPlan(n, world, r) for r in range(world)]
+
+
+def reduce_partials(buf, group=None):
+    """Sum the stacked partial [J; K] buffer over ranks in place (the path's only exchange step)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class FockEngine:
+    """J/K, LDA grid quadrature and MP2 transforms on one B200; mirrors the loop nests of hf_ksdft.py/mp2.py."""
+
+    def __init__(self, device=None, rank=0, world=1, group=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SqccError("sqcc_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.rank, self.world, self.group = rank, world, group
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.sqcc_ctx_create(self.device.index, ctypes.byref(h)))
+        self.ctx = h
+        self.n = 0
+        self.plan = None
+        self.eri = None
+        self._phi = self._w = None
+        self._use_stream()
+
+    def _use_stream(self):
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.sqcc_ctx_set_stream(self.ctx, ctypes.c_void_p(s)))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.sqcc_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ ERI ingest
+    def _alloc_shard(self, n):
+        self.n = int(n)
+        self.plan = ShardPlan(n, self.world, self.rank)
+        self.eri = torch.empty(max(self.plan.native_len, 2), dtype=torch.float64, device=self.device)
+        self._use_stream()
+        _lib.check(self.lib.sqcc_eri_attach(self.ctx, _ptr(self.eri), self.n, self.plan.ij_begin, self.plan.ij_end))
+
+    def attach_eri_synth(self, n, seed):
+        """Counter-based synthetic packed ERI, generated on the device shard by shard."""
+        self._alloc_shard(n)
+        _lib.check(self.lib.sqcc_eri_synth(self.ctx, ctypes.c_uint64(seed)))
+        return self
+
+    def attach_eri_full(self, eri_full):
+        """Pack the full [N,N,N,N] host tensor of interface_psi4.py:177-190 into this rank's shard."""
+        eri_full = np.ascontiguousarray(eri_full, dtype=np.float64)
+        n = eri_full.shape[0]
+        assert eri_full.shape == (n, n, n, n)
+        self._alloc_shard(n)
+        _lib.check(self.lib.sqcc_eri_pack_full_host(self.ctx, eri_full.ctypes.data_as(ctypes.c_void_p)))
+        return self
+
+    def attach_eri_canonical(self, packed, n, rows_per_chunk=None):
+        """Pack a canonical packed host vector (ij(ij+1)/2+kl) into this rank's shard."""
+        packed = np.ascontiguousarray(packed, dtype=np.float64)
+        self._alloc_shard(n)
+        lo, hi = self.plan.ij_begin, self.plan.ij_end
+        budget = 64 << 20  # doubles per staged chunk
+        ij = lo
+        while ij < hi:
+            e = ij
+            while e < hi and (e + 1) * (e + 2) // 2 - ij * (ij + 1) // 2 <= budget:
+                e += 1
+            e = max(e, ij + 1)
+            seg = torch.from_numpy(packed[ij * (ij + 1) // 2: e * (e + 1) // 2]).to(self.device)
+            _lib.check(self.lib.sqcc_eri_pack_canonical(self.ctx, _ptr(seg), ij, e - ij))
+            torch.cuda.current_stream().synchronize()
+            ij = e
+        return self
+
+    def eri_bytes(self):
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.sqcc_eri_bytes(self.ctx, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def eri_full(self):
+        """Expand the (unsharded) packed tensor back to the dense [N,N,N,N] host array."""
+        n = self.n
+        out = torch.empty((n, n, n, n), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.sqcc_eri_unpack_full(self.ctx, _ptr(out)))
+        return out.cpu().numpy()
+
+    def set_jk_variant(self, variant):
+        _lib.check(self.lib.sqcc_jk_set_variant(self.ctx, int(variant)))
+
+    # ------------------------------------------------------------------ J/K
+    def jk_device(self, d, want_k=True, out=None):
+        """d: cuda float64 [N,N] or [2,N,N].  Returns the stacked device buffer [1+nspin, N, N] = [J; K...]."""
+        nspin = 1 if d.dim() == 2 else 2
+        n = self.n
+        if out is None:
+            out = torch.empty((1 + (nspin if want_k else 0), n, n), dtype=torch.float64, device=self.device)
+        self._use_stream()
+        _lib.check(self.lib.sqcc_jk_build(self.ctx, _ptr(d), nspin, int(want_k), _ptr(out[0]),
+                                          _ptr(out[1]) if want_k else None))
+        reduce_partials(out, self.group)
+        return out
+
+    def jk(self, d, want_k=True):
+        """Host in / host out, reference semantics (hf_ksdft.py:483-495, :510-535).
+
+        d [N,N] -> (J, K);  d [2,N,N] -> (J(d0+d1), K[2,N,N]);  K is None when want_k is False.
+        """
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        nspin = 1 if d.ndim == 2 else 2
+        n = self.n
+        if self.world == 1:
+            j = np.empty((n, n))
+            k = np.empty((nspin, n, n)) if want_k else None
+            self._use_stream()
+            _lib.check(self.lib.sqcc_jk_build_host(
+                self.ctx, d.ctypes.data_as(ctypes.c_void_p), nspin, int(want_k),
+                j.ctypes.data_as(ctypes.c_void_p), k.ctypes.data_as(ctypes.c_void_p) if want_k else None))
+        else:
+            out = self.jk_device(torch.from_numpy(d).to(self.device), want_k).cpu().numpy()
+            j, k = out[0], (out[1:] if want_k else None)
+        if want_k and d.ndim == 2:
+            k = k[0]
+        return j, k
+
+    # ------------------------------------------------------------------ LDA grid
+    def attach_grid(self, phi, w):
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        self._phi = torch.from_numpy(phi).to(self.device)
+        self._w = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64)).to(self.device)
+        _lib.check(self.lib.sqcc_grid_attach(self.ctx, _ptr(self._phi), _ptr(self._w), phi.shape[0], phi.shape[1]))
+        return self
+
+    def lda_vxc(self, d, want_rho=False):
+        """Rows G+H+I fused: d [N,N] -> (Vxc [N,N], Exc, rho [G]|None); d [2,N,N] -> ([2,N,N], Exc, [2,G]|None)."""
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        nspin = 1 if d.ndim == 2 else 2
+        n, g = self._phi.shape[1], self._phi.shape[0]
+        v = np.empty((nspin, n, n))
+        exc = ctypes.c_double()
+        rho = np.empty((nspin, g)) if want_rho else None
+        self._use_stream()
+        _lib.check(self.lib.sqcc_lda_vxc_host(self.ctx, d.ctypes.data_as(ctypes.c_void_p), nspin,
+                                              v.ctypes.data_as(ctypes.c_void_p), ctypes.byref(exc),
+                                              rho.ctypes.data_as(ctypes.c_void_p) if want_rho else None))
+        if d.ndim == 2:
+            return v[0], exc.value, (rho[0] if want_rho else None)
+        return v, exc.value, rho
+
+    def grid_quadrature(self, v):
+        """V_pq = sum_n phi_np (w_n v_n) phi_nq for a caller-supplied potential on the attached points."""
+        n = self._phi.shape[1]
+        vt = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(self.device)
+        out = torch.empty((n, n), dtype=torch.float64, device=self.device)
+        self._use_stream()
+        _lib.check(self.lib.sqcc_grid_quadrature(self.ctx, _ptr(vt), _ptr(out)))
+        return out.cpu().numpy()
+
+    def grid_rho(self, d):
+        dt = torch.from_numpy(np.ascontiguousarray(d, dtype=np.float64)).to(self.device)
+        out = torch.empty(self._phi.shape[0], dtype=torch.float64, device=self.device)
+        self._use_stream()
+        _lib.check(self.lib.sqcc_grid_rho(self.ctx, _ptr(dt), _ptr(out)))
+        return out.cpu().numpy()
+
+    # ------------------------------------------------------------------ MP2 / AO->MO
+    def mp2_corr(self, c, eps, n_occ, want_iajb=False):
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        eps = np.ascontiguousarray(eps, dtype=np.float64)
+        n = self.n
+        nv = n - n_occ
+        e = ctypes.c_double()
+        iajb = np.empty((n_occ, nv, n_occ, nv)) if want_iajb else None
+        self._use_stream()
+        _lib.check(self.lib.sqcc_mp2_host(self.ctx, c.ctypes.data_as(ctypes.c_void_p),
+                                          eps.ctypes.data_as(ctypes.c_void_p), int(n_occ), ctypes.byref(e),
+                                          iajb.ctypes.data_as(ctypes.c_void_p) if want_iajb else None))
+        return (e.value, iajb) if want_iajb else e.value
+
+    def ao2mo(self, c1, c2, c3, c4):
+        """(pq|rs) -> (ab|cd) for four column blocks of one [N,N] AO x MO matrix given as (matrix, lo, hi)."""
+        n = self.n
+        mats = []
+        for c in (c1, c2, c3, c4):
+            m = np.zeros((n, n))
+            m[:, :c.shape[1]] = c
+            mats.append(torch.from_numpy(m).to(self.device))
+        dims = [c.shape[1] for c in (c1, c2, c3, c4)]
+        out = torch.empty(dims, dtype=torch.float64, device=self.device)
+        self._use_stream()
+        _lib.check(self.lib.sqcc_ao2mo(self.ctx, _ptr(mats[0]), dims[0], _ptr(mats[1]), dims[1], _ptr(mats[2]),
+                                       dims[2], _ptr(mats[3]), dims[3], _ptr(out)))
+        return out.cpu().numpy()
+
+    # ------------------------------------------------------------------ instrumentation
+    def timings(self):
+        buf = (ctypes.c_double * 8)()
+        _lib.check(self.lib.sqcc_get_timings(self.ctx, buf, 8))
+        names = ["jk_kernel", "jk_finalize", "rho", "vxc", "mp2_transform", "mp2_energy", "t6", "t7"]
+        return {k: buf[i] for i, k in enumerate(names)}
+
+    def launch_count(self):
+        return int(self.lib.sqcc_launch_count(self.ctx))
+
+    def synchronize(self):
+        _lib.check(self.lib.sqcc_ctx_synchronize(self.ctx))

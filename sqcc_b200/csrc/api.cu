@@ -1,0 +1,417 @@
+// C ABI of libsqcc_b200.so (see include/sqcc_b200.h).  Thin: argument checks, staging, dispatch.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sqcc {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+
+int ensure_io(sqcc_ctx *ctx, size_t bytes)
+{
+    if (ctx->io_bytes >= bytes) return SQCC_OK;
+    if (ctx->d_io) cudaFree(ctx->d_io);
+    ctx->d_io = nullptr;
+    ctx->io_bytes = 0;
+    SQCC_CUDA(cudaMalloc(&ctx->d_io, bytes));
+    ctx->io_bytes = bytes;
+    return SQCC_OK;
+}
+
+int ensure_pin(sqcc_ctx *ctx, size_t bytes)
+{
+    if (ctx->pin_bytes >= bytes) return SQCC_OK;
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    ctx->h_pin = nullptr;
+    ctx->pin_bytes = 0;
+    SQCC_CUDA(cudaMallocHost(&ctx->h_pin, bytes));
+    ctx->pin_bytes = bytes;
+    return SQCC_OK;
+}
+
+int timer_start(sqcc_ctx *ctx, int slot)
+{
+    Timer &t = ctx->timers[slot];
+    if (!t.a) {
+        SQCC_CUDA(cudaEventCreate(&t.a));
+        SQCC_CUDA(cudaEventCreate(&t.b));
+    }
+    SQCC_CUDA(cudaEventRecord(t.a, ctx->stream));
+    return SQCC_OK;
+}
+
+int timer_stop(sqcc_ctx *ctx, int slot)
+{
+    Timer &t = ctx->timers[slot];
+    SQCC_CUDA(cudaEventRecord(t.b, ctx->stream));
+    t.used = true;
+    return SQCC_OK;
+}
+
+// Offset (doubles) of row ij = (i, j) from the start of the full native tensor.
+static int64_t global_row_offset(int64_t ij)
+{
+    int i, j;
+    int64_t t = (int64_t)((sqrt(8.0 * (double)ij + 1.0) - 1.0) * 0.5);
+    while (t * (t + 1) / 2 > ij) --t;
+    while ((t + 1) * (t + 2) / 2 <= ij) ++t;
+    i = (int)t;
+    j = (int)(ij - t * (t + 1) / 2);
+    return iblock_offset(i) + (int64_t)j * subrow_offset(i) + subrow_offset(j);
+}
+
+// Row index at which shard g of `world` starts: equal-area cut with row granularity.
+static int64_t shard_cut(int n, int world, int g)
+{
+    const int64_t np_ = (int64_t)n * (n + 1) / 2;
+    if (g <= 0) return 0;
+    if (g >= world) return np_;
+    const double target = (double)global_row_offset(np_) * (double)g / (double)world;
+    int64_t lo = 0, hi = np_;
+    while (lo < hi) {  // first row whose start offset >= target
+        int64_t mid = (lo + hi) / 2;
+        if ((double)global_row_offset(mid) < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace sqcc
+
+using namespace sqcc;
+
+extern "C" {
+
+int sqcc_version(void) { return 100; }
+const char *sqcc_last_error(void) { return g_error.c_str(); }
+
+int sqcc_device_count(int *count)
+{
+    SQCC_REQUIRE(count, "null count");
+    SQCC_CUDA(cudaGetDeviceCount(count));
+    return SQCC_OK;
+}
+
+int sqcc_ctx_create(int device, sqcc_ctx **out)
+{
+    SQCC_REQUIRE(out, "null out");
+    SQCC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SQCC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("libsqcc_b200 is built for sm_100a only; device is ") + prop.name);
+        return SQCC_ERR_UNSUPPORTED;
+    }
+    sqcc_ctx *ctx = new sqcc_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return SQCC_OK;
+}
+
+int sqcc_ctx_destroy(sqcc_ctx *ctx)
+{
+    if (!ctx) return SQCC_OK;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_rowoff);
+    for (auto &sc : ctx->sched) {
+        cudaFree(sc.d_rowblocks);
+        cudaFree(sc.d_tasks);
+    }
+    cudaFree(ctx->d_dwork);
+    cudaFree(ctx->d_acc);
+    cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_io);
+    cudaFree(ctx->d_gridwork);
+    cudaFree(ctx->d_mp2work);
+    cudaFree(ctx->d_mp2out);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    for (auto &t : ctx->timers) {
+        if (t.a) cudaEventDestroy(t.a);
+        if (t.b) cudaEventDestroy(t.b);
+    }
+    delete ctx;
+    return SQCC_OK;
+}
+
+int sqcc_ctx_set_stream(sqcc_ctx *ctx, void *cuda_stream)
+{
+    SQCC_REQUIRE(ctx, "null ctx");
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return SQCC_OK;
+}
+
+int sqcc_ctx_synchronize(sqcc_ctx *ctx)
+{
+    SQCC_REQUIRE(ctx, "null ctx");
+    SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SQCC_OK;
+}
+
+int64_t sqcc_npair(int n) { return (int64_t)n * (n + 1) / 2; }
+int64_t sqcc_nquad(int n)
+{
+    int64_t p = sqcc_npair(n);
+    return p * (p + 1) / 2;
+}
+
+int sqcc_shard_rows(int n, int world, int rank, int64_t *ij_begin, int64_t *ij_end)
+{
+    SQCC_REQUIRE(n > 0 && world > 0 && rank >= 0 && rank < world && ij_begin && ij_end, "bad shard arguments");
+    int64_t a = shard_cut(n, world, rank), b = shard_cut(n, world, rank + 1);
+    if (b < a) b = a;
+    *ij_begin = a;
+    *ij_end = b;
+    return SQCC_OK;
+}
+
+int64_t sqcc_native_len(int n, int64_t ij_begin, int64_t ij_end)
+{
+    if (n <= 0 || ij_begin < 0 || ij_end < ij_begin || ij_end > sqcc_npair(n)) return -1;
+    return global_row_offset(ij_end) - global_row_offset(ij_begin);
+}
+
+int64_t sqcc_native_offset(int n, int64_t ij_begin, int i, int j, int k, int l)
+{
+    if (i < 0 || i >= n || j < 0 || j > i || k < 0 || l < 0 || l > k) return -1;
+    if (pair_index(k, l) > pair_index(i, j) || pair_index(i, j) < ij_begin) return -1;
+    return global_row_offset(pair_index(i, j)) - global_row_offset(ij_begin) + subrow_offset(k) + l;
+}
+
+static int row_i(int64_t ij)
+{
+    int64_t t = (int64_t)((sqrt(8.0 * (double)ij + 1.0) - 1.0) * 0.5);
+    while (t * (t + 1) / 2 > ij) --t;
+    while ((t + 1) * (t + 2) / 2 <= ij) ++t;
+    return (int)t;
+}
+
+int sqcc_eri_attach(sqcc_ctx *ctx, double *d_native, int n, int64_t ij_begin, int64_t ij_end)
+{
+    SQCC_REQUIRE(ctx && d_native, "null ctx / buffer");
+    SQCC_REQUIRE(n > 0 && n <= 4096, "N out of range");
+    SQCC_REQUIRE(ij_begin >= 0 && ij_end >= ij_begin && ij_end <= sqcc_npair(n), "bad row range");
+    const int a = row_i(ij_begin), b = ij_end > ij_begin ? row_i(ij_end - 1) + 1 : a;
+    SQCC_REQUIRE((reinterpret_cast<uintptr_t>(d_native) & 15) == 0, "ERI buffer must be 16-byte aligned");
+    SQCC_CUDA(cudaSetDevice(ctx->device));
+    ctx->d_eri = d_native;
+    ctx->n = n;
+    ctx->ldd = (n + 3) & ~3;
+    ctx->ij_begin = ij_begin;
+    ctx->ij_end = ij_end;
+    ctx->i_begin = a;
+    ctx->i_end = b;
+    SQCC_TRY(eri_build_tables(ctx));
+    SQCC_TRY(jk_build_schedule(ctx));
+    return SQCC_OK;
+}
+
+int sqcc_eri_synth(sqcc_ctx *ctx, uint64_t seed)
+{
+    SQCC_REQUIRE(ctx && ctx->d_eri, "no ERI attached");
+    SQCC_CUDA(cudaMemsetAsync(ctx->d_eri, 0, sizeof(double) * ctx->native_len, ctx->stream));
+    return eri_synth(ctx, seed);
+}
+
+int sqcc_eri_pack_full_slab(sqcc_ctx *ctx, const double *d_slab, int p0, int np)
+{
+    SQCC_REQUIRE(ctx && ctx->d_eri && d_slab, "no ERI attached / null slab");
+    SQCC_REQUIRE(p0 >= 0 && np > 0 && p0 + np <= ctx->n, "slab range out of bounds");
+    return eri_pack_full_slab(ctx, d_slab, p0, np);
+}
+
+int sqcc_eri_pack_full_host(sqcc_ctx *ctx, const double *h_eri_full)
+{
+    SQCC_REQUIRE(ctx && ctx->d_eri && h_eri_full, "no ERI attached / null tensor");
+    const int n = ctx->n;
+    const size_t slab = (size_t)n * n * n;  // doubles per p
+    // slabs of up to ~256 MB, double-buffered through pinned memory
+    int np = (int)((size_t)(256u << 20) / (slab * sizeof(double)));
+    if (np < 1) np = 1;
+    if (np > n) np = n;
+    SQCC_TRY(ensure_pin(ctx, 2 * slab * np * sizeof(double)));
+    SQCC_TRY(ensure_io(ctx, 2 * slab * np * sizeof(double)));
+    cudaEvent_t done[2];
+    SQCC_CUDA(cudaEventCreate(&done[0]));
+    SQCC_CUDA(cudaEventCreate(&done[1]));
+    int buf = 0, issued = 0;
+    for (int p0 = ctx->i_begin; p0 < ctx->i_end; p0 += np, buf ^= 1, ++issued) {
+        int cnt = p0 + np <= ctx->i_end ? np : ctx->i_end - p0;
+        double *hp = ctx->h_pin + (size_t)buf * slab * np;
+        double *dp = ctx->d_io + (size_t)buf * slab * np;
+        if (issued >= 2) SQCC_CUDA(cudaEventSynchronize(done[buf]));
+        memcpy(hp, h_eri_full + (size_t)p0 * slab, (size_t)cnt * slab * sizeof(double));
+        SQCC_CUDA(cudaMemcpyAsync(dp, hp, (size_t)cnt * slab * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        SQCC_TRY(eri_pack_full_slab(ctx, dp, p0, cnt));
+        SQCC_CUDA(cudaEventRecord(done[buf], ctx->stream));
+    }
+    SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaEventDestroy(done[0]);
+    cudaEventDestroy(done[1]);
+    return SQCC_OK;
+}
+
+int sqcc_eri_pack_canonical(sqcc_ctx *ctx, const double *d_rows, int64_t ij0, int64_t nrows)
+{
+    SQCC_REQUIRE(ctx && ctx->d_eri && d_rows, "no ERI attached / null rows");
+    SQCC_REQUIRE(ij0 >= 0 && nrows > 0 && ij0 + nrows <= sqcc_npair(ctx->n), "row range out of bounds");
+    return eri_pack_canonical(ctx, d_rows, ij0, nrows);
+}
+
+int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full)
+{
+    SQCC_REQUIRE(ctx && d_eri_full, "null ctx / output");
+    return eri_unpack_full(ctx, d_eri_full);
+}
+
+int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant)
+{
+    SQCC_REQUIRE(ctx && (variant == 0 || variant == 1), "variant must be 0 or 1");
+    ctx->jk_variant = variant;
+    return SQCC_OK;
+}
+
+int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_J, double *d_K)
+{
+    SQCC_REQUIRE(ctx, "null ctx");
+    return jk_build(ctx, d_D, nspin, want_k, d_J, d_K);
+}
+
+int sqcc_jk_build_host(sqcc_ctx *ctx, const double *h_D, int nspin, int want_k, double *h_J, double *h_K)
+{
+    SQCC_REQUIRE(ctx && h_D && h_J && (!want_k || h_K), "null ctx / buffers");
+    SQCC_REQUIRE(nspin == 1 || nspin == 2, "nspin must be 1 or 2");
+    const size_t nn = (size_t)ctx->n * ctx->n;
+    // staging layout: [D nspin*nn][J nn][K nspin*nn]
+    const size_t total = (2 * (size_t)nspin + 1) * nn;
+    SQCC_TRY(ensure_io(ctx, total * sizeof(double)));
+    SQCC_TRY(ensure_pin(ctx, total * sizeof(double)));
+    double *dD = ctx->d_io, *dJ = dD + nspin * nn, *dK = dJ + nn;
+    memcpy(ctx->h_pin, h_D, nspin * nn * sizeof(double));
+    SQCC_CUDA(cudaMemcpyAsync(dD, ctx->h_pin, nspin * nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SQCC_TRY(jk_build(ctx, dD, nspin, want_k, dJ, dK));
+    const size_t out = (want_k ? (size_t)nspin + 1 : 1) * nn;
+    SQCC_CUDA(cudaMemcpyAsync(ctx->h_pin + nspin * nn, dJ, out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(h_J, ctx->h_pin + nspin * nn, nn * sizeof(double));
+    if (want_k) memcpy(h_K, ctx->h_pin + (nspin + 1) * nn, nspin * nn * sizeof(double));
+    return SQCC_OK;
+}
+
+int sqcc_grid_attach(sqcc_ctx *ctx, const double *d_phi, const double *d_w, int64_t G, int n)
+{
+    SQCC_REQUIRE(ctx && d_phi && d_w && G > 0 && n > 0, "bad grid arguments");
+    ctx->d_phi = d_phi;
+    ctx->d_w = d_w;
+    ctx->G = G;
+    ctx->grid_n = n;
+    return SQCC_OK;
+}
+
+int sqcc_lda_vxc(sqcc_ctx *ctx, const double *d_D, int nspin, double *d_Vxc, double *d_Exc, double *d_rho)
+{
+    SQCC_REQUIRE(ctx && ctx->d_phi, "no grid attached (sqcc_grid_attach)");
+    SQCC_REQUIRE(d_D && d_Vxc && d_Exc && (nspin == 1 || nspin == 2), "bad lda_vxc arguments");
+    return lda_vxc(ctx, d_D, nspin, d_Vxc, d_Exc, d_rho);
+}
+
+int sqcc_lda_vxc_host(sqcc_ctx *ctx, const double *h_D, int nspin, double *h_Vxc, double *h_Exc, double *h_rho)
+{
+    SQCC_REQUIRE(ctx && ctx->d_phi, "no grid attached (sqcc_grid_attach)");
+    SQCC_REQUIRE(h_D && h_Vxc && h_Exc && (nspin == 1 || nspin == 2), "bad lda_vxc arguments");
+    const size_t nn = (size_t)ctx->grid_n * ctx->grid_n;
+    const size_t g = (size_t)ctx->G;
+    // staging: [D nspin*nn][Vxc nspin*nn][Exc 1 (+1 pad)][rho nspin*G]
+    const size_t small = 2 * nspin * nn + 2;
+    SQCC_TRY(ensure_io(ctx, (small + nspin * g) * sizeof(double)));
+    SQCC_TRY(ensure_pin(ctx, (small + (h_rho ? nspin * g : 0)) * sizeof(double)));
+    double *dD = ctx->d_io, *dV = dD + nspin * nn, *dE = dV + nspin * nn, *dR = dE + 2;
+    memcpy(ctx->h_pin, h_D, nspin * nn * sizeof(double));
+    SQCC_CUDA(cudaMemcpyAsync(dD, ctx->h_pin, nspin * nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SQCC_TRY(lda_vxc(ctx, dD, nspin, dV, dE, dR));
+    size_t out = nspin * nn + 2 + (h_rho ? nspin * g : 0);
+    SQCC_CUDA(cudaMemcpyAsync(ctx->h_pin + nspin * nn, dV, out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(h_Vxc, ctx->h_pin + nspin * nn, nspin * nn * sizeof(double));
+    *h_Exc = ctx->h_pin[2 * nspin * nn];
+    if (h_rho) memcpy(h_rho, ctx->h_pin + small, nspin * g * sizeof(double));
+    return SQCC_OK;
+}
+
+int sqcc_grid_quadrature(sqcc_ctx *ctx, const double *d_v, double *d_V)
+{
+    SQCC_REQUIRE(ctx && ctx->d_phi && d_v && d_V, "no grid attached / null pointers");
+    return grid_quadrature(ctx, d_v, d_V);
+}
+
+int sqcc_grid_rho(sqcc_ctx *ctx, const double *d_D, double *d_rho)
+{
+    SQCC_REQUIRE(ctx && ctx->d_phi && d_D && d_rho, "no grid attached / null pointers");
+    return grid_rho(ctx, d_D, d_rho);
+}
+
+int sqcc_ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2, const double *d_C3, int n3,
+               const double *d_C4, int n4, double *d_out)
+{
+    SQCC_REQUIRE(ctx && ctx->d_eri && d_C1 && d_C2 && d_C3 && d_C4 && d_out, "no ERI attached / null pointers");
+    SQCC_REQUIRE(n1 > 0 && n2 > 0 && n3 > 0 && n4 > 0, "bad MO block sizes");
+    return ao2mo(ctx, d_C1, n1, d_C2, n2, d_C3, n3, d_C4, n4, d_out);
+}
+
+int sqcc_mp2(sqcc_ctx *ctx, const double *d_C, const double *d_eps, int n_occ, double *d_ecorr, double *d_iajb)
+{
+    SQCC_REQUIRE(ctx && ctx->d_eri && d_C && d_eps && d_ecorr, "no ERI attached / null pointers");
+    SQCC_REQUIRE(n_occ > 0 && n_occ < ctx->n, "n_occ out of range");
+    return mp2(ctx, d_C, d_eps, n_occ, d_ecorr, d_iajb);
+}
+
+int sqcc_mp2_host(sqcc_ctx *ctx, const double *h_C, const double *h_eps, int n_occ, double *h_ecorr, double *h_iajb)
+{
+    SQCC_REQUIRE(ctx && ctx->d_eri && h_C && h_eps && h_ecorr, "no ERI attached / null pointers");
+    SQCC_REQUIRE(n_occ > 0 && n_occ < ctx->n, "n_occ out of range");
+    const size_t n = ctx->n, nn = n * n, nv = n - n_occ;
+    const size_t nout = h_iajb ? (size_t)n_occ * nv * n_occ * nv : 0;
+    SQCC_TRY(ensure_io(ctx, (nn + n + 2 + nout) * sizeof(double)));
+    SQCC_TRY(ensure_pin(ctx, (nn + n + 2 + nout) * sizeof(double)));
+    double *dC = ctx->d_io, *dE = dC + nn, *dX = dE + n, *dO = dX + 2;
+    memcpy(ctx->h_pin, h_C, nn * sizeof(double));
+    memcpy(ctx->h_pin + nn, h_eps, n * sizeof(double));
+    SQCC_CUDA(cudaMemcpyAsync(dC, ctx->h_pin, (nn + n) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SQCC_TRY(mp2(ctx, dC, dE, n_occ, dX, h_iajb ? dO : nullptr));
+    SQCC_CUDA(cudaMemcpyAsync(ctx->h_pin + nn + n, dX, (2 + nout) * sizeof(double), cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+    *h_ecorr = ctx->h_pin[nn + n];
+    if (h_iajb) memcpy(h_iajb, ctx->h_pin + nn + n + 2, nout * sizeof(double));
+    return SQCC_OK;
+}
+
+int sqcc_get_timings(sqcc_ctx *ctx, double *ms, int n)
+{
+    SQCC_REQUIRE(ctx && ms && n > 0, "bad timing arguments");
+    int m = n < 8 ? n : 8;
+    for (int s = 0; s < m; ++s) {
+        ms[s] = -1.0;
+        sqcc::Timer &t = ctx->timers[s];
+        if (t.used) {
+            SQCC_CUDA(cudaEventSynchronize(t.b));
+            float f = 0.f;
+            SQCC_CUDA(cudaEventElapsedTime(&f, t.a, t.b));
+            ms[s] = f;
+        }
+    }
+    return m;
+}
+
+int64_t sqcc_launch_count(sqcc_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int sqcc_eri_bytes(sqcc_ctx *ctx, int64_t *native_bytes, int64_t *algorithmic_bytes)
+{
+    SQCC_REQUIRE(ctx && ctx->d_eri, "no ERI attached");
+    if (native_bytes) *native_bytes = ctx->native_len * 8;
+    if (algorithmic_bytes) *algorithmic_bytes = ctx->n_unique * 8;
+    return SQCC_OK;
+}
+
+}  // extern "C"
