@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nbf", type=int, default=494, help="basis functions of the synthetic packed ERI")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary (N=222/264, UHF, LDA, MP2) measurements")
+    ap.add_argument("--variant", type=int, default=0, help="J/K kernel: 0 TMA pipeline, 2 direct-load, 1 simple")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     return ap.parse_args()
 
@@ -205,6 +206,7 @@ def main():
     n = args.nbf
     eng = FockEngine(device=local, rank=rank, world=world)
     eng.attach_eri_synth(n, SEED)
+    eng.set_jk_variant(args.variant)
     eng.synchronize()
     d_host = density_rhf(n, NOCC.get(n, max(1, n // 10)), 7)
     d_dev = torch.from_numpy(d_host).to(eng.device)

@@ -85,7 +85,8 @@ int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full);
 int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_J, double *d_K);
 /* Same through host buffers (H2D of D, D2H of J/K inside; stream-synchronous). */
 int sqcc_jk_build_host(sqcc_ctx *ctx, const double *h_D, int nspin, int want_k, double *h_J, double *h_K);
-/* Select the kernel: 0 = tiled register kernel (default), 1 = simple atomics kernel (cross-check). */
+/* Select the kernel: 0 = TMA-pipelined tiled kernel (default), 1 = simple atomics kernel (cross-check),
+ * 2 = tiled kernel with direct 128-bit global loads (no TMA staging). */
 int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant);
 
 /* ---- LDA exchange grid quadrature: replaces hf_ksdft.py:426-440, :634-646 (rho), ksdft_functional.py

@@ -115,6 +115,7 @@ int sqcc_ctx_destroy(sqcc_ctx *ctx)
     if (!ctx) return SQCC_OK;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_rowoff);
+    cudaFree(ctx->d_ioff);
     for (auto &sc : ctx->sched) {
         cudaFree(sc.d_rowblocks);
         cudaFree(sc.d_tasks);
@@ -267,7 +268,7 @@ int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full)
 
 int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant)
 {
-    SQCC_REQUIRE(ctx && (variant == 0 || variant == 1), "variant must be 0 or 1");
+    SQCC_REQUIRE(ctx && variant >= 0 && variant <= 2, "variant must be 0 (TMA), 1 (simple) or 2 (direct-load)");
     ctx->jk_variant = variant;
     return SQCC_OK;
 }

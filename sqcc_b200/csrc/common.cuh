@@ -99,6 +99,8 @@ struct sqcc_ctx {
     int64_t native_len = 0;
     int64_t n_unique = 0;
     int64_t *d_rowoff = nullptr;  // [npair_local + 1] offsets relative to shard start
+    int64_t *d_ioff = nullptr;    // [n + 1] offsets of rows (i,0) in the full native tensor
+    int64_t shard_base = 0;       // offset of the shard's first row in the full native tensor
     sqcc::JKSchedule sched[2];    // [0]: NI=4,NJ=2 (nspin 1);  [1]: NI=2,NJ=2 (nspin 2)
     int jk_variant = 0;
 

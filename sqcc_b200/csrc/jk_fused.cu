@@ -26,6 +26,8 @@ namespace sqcc {
 struct JKParams {
     const double *P;
     const int64_t *rowoff;
+    const int64_t *ioff;   // [n+1] offset of row (i,0) from the start of the full native tensor
+    int64_t shard_base;    // offset of this shard's first row in the full native tensor
     int64_t ij_begin, ij_end;
     int n, ldd;
     const double *d2;   // [n][ldd]   2*(Da+Db)
@@ -311,6 +313,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_tiled_kernel(const JKParams 
     }
 }
 
+}  // namespace sqcc
+#include "jk_pipe.cuh"
+namespace sqcc {
+
 // ---- simple cross-check kernel: one CTA per row, one global atomic per contribution ------------------
 template <int NSPIN, bool WANTK>
 __global__ void __launch_bounds__(256) jk_simple_kernel(const JKParams p, int64_t nrows, int i_begin)
@@ -461,6 +467,39 @@ int jk_build_schedule(sqcc_ctx *ctx)
     SQCC_CUDA(cudaMalloc(&ctx->d_dwork, sizeof(double) * 3 * nl));
     SQCC_CUDA(cudaMalloc(&ctx->d_acc, sizeof(double) * 3 * nl));
     if (!ctx->d_counter) SQCC_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+    // row (i,0) offsets for arithmetic row addressing in the TMA kernel
+    std::vector<int64_t> ioff(ctx->n + 1);
+    ioff[0] = 0;
+    for (int i = 0; i < ctx->n; ++i) ioff[i + 1] = ioff[i] + (int64_t)(i + 1) * subrow_offset(i) + subrow_offset(i + 1);
+    if (ctx->d_ioff) cudaFree(ctx->d_ioff);
+    ctx->d_ioff = nullptr;
+    SQCC_CUDA(cudaMalloc(&ctx->d_ioff, sizeof(int64_t) * (ctx->n + 1)));
+    SQCC_CUDA(cudaMemcpyAsync(ctx->d_ioff, ioff.data(), sizeof(int64_t) * (ctx->n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+    {
+        int i = ctx->i_begin;
+        int64_t j = ctx->ij_begin - pair_index(i, 0);
+        ctx->shard_base = ioff[i] + j * subrow_offset(i) + subrow_offset(j);
+    }
+    return SQCC_OK;
+}
+
+template <int NI, int NJ, int NSPIN, bool WANTK>
+static int launch_pipe(sqcc_ctx *ctx, const JKParams &p)
+{
+    constexpr int WARPS = 8, STAGES = 3;
+    const size_t smem = (size_t)WARPS * jk_pipe_warp_bytes<NI, NJ, STAGES>();
+    auto kern = jk_pipe_kernel<NI, NJ, NSPIN, WANTK, WARPS, STAGES>;
+    SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SQCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = ctx->sm_count * per_sm;
+    int max_useful = (p.ntasks + WARPS - 1) / WARPS;
+    if (grid > max_useful) grid = max_useful > 0 ? max_useful : 1;
+    kern<<<grid, WARPS * 32, smem, ctx->stream>>>(p);
+    ctx->launches++;
+    SQCC_CUDA(cudaGetLastError());
     return SQCC_OK;
 }
 
@@ -499,6 +538,8 @@ int jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_
     JKParams p;
     p.P = ctx->d_eri;
     p.rowoff = ctx->d_rowoff;
+    p.ioff = ctx->d_ioff;
+    p.shard_base = ctx->shard_base;
     p.ij_begin = ctx->ij_begin;
     p.ij_end = ctx->ij_end;
     p.n = n;
@@ -525,6 +566,13 @@ int jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_
             jk_simple_kernel<2, true><<<grid, 256, 0, ctx->stream>>>(p, nrows, ctx->i_begin);
         ctx->launches++;
         SQCC_CUDA(cudaGetLastError());
+    } else if (ctx->jk_variant == 0 && p.ntasks > 0) {
+        if (!want_k)
+            SQCC_TRY((launch_pipe<JK_NI, JK_NJ, 1, false>(ctx, p)));
+        else if (nspin == 1)
+            SQCC_TRY((launch_pipe<JK_NI, JK_NJ, 1, true>(ctx, p)));
+        else
+            SQCC_TRY((launch_pipe<2, 2, 2, true>(ctx, p)));
     } else if (p.ntasks > 0) {
         if (!want_k)
             SQCC_TRY((launch_tiled<JK_NI, JK_NJ, 1, false>(ctx, p)));

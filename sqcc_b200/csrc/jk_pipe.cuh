@@ -1,0 +1,353 @@
+// Fused J/K kernel, software-pipelined variant (default).  Included by jk_fused.cu.
+//
+// Same warp-task decomposition as jk_tiled_kernel (see jk_fused.cu): a warp owns (k-range of JK_KN sub-rows) x
+// (64-column l-chunk, two columns per lane) and sweeps a list of NI x NJ row-blocks.  Differences:
+//   * the ERI stream is prefetched STAGES-1 sub-rows ahead into a per-warp shared-memory ring with 16-byte
+//     cp.async (LDGSTS.128, L2-only).  Every lane copies and later reads back only its own 16 bytes of each of
+//     the NI*NJ rows, so the ring needs no barriers (cp.async.wait_group is per thread), costs no registers and
+//     keeps WARPS * (STAGES-1) * (NI*NJ+1) * 512 B in flight per SM.  Lanes outside a triangular sub-row use
+//     the zero-fill form, so the consumer loop is mask free.  The matching D2[k, l-chunk] density tile row
+//     rides in the same ring stage (one more 16-byte copy per lane).  The pipeline runs across the row-block
+//     boundaries of a task.
+//   * the warp-uniform operands D[i,k], D[j,k] of a row-block are staged once per row-block in shared memory
+//     and read back as broadcast 128-bit loads.
+//   * the K~[i,k] / K~[j,k] lane partials are reduced across the warp through a conflict-free shared-memory
+//     transpose (8 stores + 8 loads + 2 shuffles per sub-row) instead of a select-heavy shuffle butterfly.
+// A TMA-only ring (cp.async.bulk per 512-byte piece + mbarrier) was measured slower: 512-byte bulk copies are
+// limited by the TMA issue rate (3.6 TB/s J-only against 6.0 TB/s with this cp.async ring, profiles/).
+#pragma once
+
+namespace sqcc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void red_add_if(bool pred, double *ptr, double v)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(ptr),
+        "d"(v), "r"((uint32_t)pred)
+        : "memory");
+}
+
+constexpr int JK_RED_STRIDE = 36;  // value stride of the reduction scratch (== 4 mod 16, >= 3*9+8)
+
+template <int NI, int NJ, int STAGES>
+constexpr int jk_pipe_warp_bytes()
+{
+    // J~ slab + ring[STAGES][NI*NJ+1][512 B] + uniform-operand staging [KN][8] + reduction scratch [8][36]
+    return JK_KN * 32 * 16 + STAGES * (NI * NJ + 1) * 512 + JK_KN * 8 * 8 + 8 * JK_RED_STRIDE * 8;
+}
+
+template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p)
+{
+    constexpr int R = NI * NJ;
+    constexpr int RS = R + 1;  // ring rows per stage: R ERI rows + the D2 tile row
+    constexpr int WARP_BYTES = jk_pipe_warp_bytes<NI, NJ, STAGES>();
+    constexpr int NS = WANTK ? NSPIN : 1;
+    constexpr int NV = NS * (NI + NJ);  // lane-partial values reduced per sub-row
+    static_assert(NV <= 8, "reduction scratch holds 8 values");
+    constexpr int VJ = next_pow2(NI * NJ);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wbase = smem_raw + (size_t)warp * WARP_BYTES;
+    double2 *s_jt = reinterpret_cast<double2 *>(wbase);              // [KN][32]
+    double2 *ring = s_jt + JK_KN * 32;                               // [STAGES][RS][32]
+    double *s_u = reinterpret_cast<double *>(ring + STAGES * RS * 32);  // [KN][8]
+    double *s_red = s_u + JK_KN * 8;                                 // [8][JK_RED_STRIDE]
+    const uint32_t ring_u32 = smem_u32(ring) + 16u * lane;
+    const int n = p.n, ldd = p.ldd;
+    const size_t nl = (size_t)n * ldd;
+    uint32_t stage_w = 0, stage_r = 0;  // ring write / read positions, persist across tasks
+
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(p.counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= (unsigned)p.ntasks) break;
+        const JKTask task = p.tasks[t];
+        const int k0 = task.k0;
+        const int cbase = task.chunk * JK_CHUNK;
+        const int l0 = cbase + 2 * lane;
+        const bool lane_in = l0 < ldd;
+        const int kk_lo = cbase > k0 ? cbase - k0 : 0;
+        const int kk_hi = (k0 + JK_KN <= n) ? JK_KN : (n - k0);
+        const int nkk = kk_hi - kk_lo;
+        const bool full_chunk = k0 >= cbase + JK_CHUNK - 1;
+        if (nkk <= 0) continue;
+        const int niter = task.rb_count * nkk;
+
+#pragma unroll 4
+        for (int kk = 0; kk < JK_KN; ++kk) s_jt[kk * 32 + lane] = make_double2(0.0, 0.0);
+
+        // row-block list of the task, one entry per lane (rb_count <= 32)
+        int my_i0 = 0, my_j0 = 0;
+        if (lane < task.rb_count) {
+            const RowBlock rbk = p.rowblocks[task.rb_begin + lane];
+            my_i0 = rbk.i0;
+            my_j0 = rbk.j0;
+        }
+        // D2 tile pointer of this lane (row k0, columns l0, l0+1); lanes past the matrix edge zero-fill
+        const double *d2p = p.d2 + (size_t)k0 * ldd + (lane_in ? l0 : 0);
+
+        // ---- producer: this lane's 16 bytes of each row of the producer's row-block, one sub-row per call
+        int prod_it = 0, prod_rbi = -1, prod_kk = kk_hi;  // forces a row-block load on the first issue
+        int prod_i0 = 0, prod_j0 = 0, prod_mode = 2;      // 0: unmasked, 1: one mask (l0 <= k), 2: per-row masks
+        const double *pbase = p.P;
+        int poff[R];   // element offsets of the rows relative to pbase (fit 32 bits: rows of <= NI adjacent i)
+        bool prv[R];
+        auto issue_next = [&]() {
+            if (prod_kk == kk_hi) {  // advance to the next row-block
+                prod_kk = kk_lo;
+                ++prod_rbi;
+                prod_i0 = __shfl_sync(0xffffffffu, my_i0, prod_rbi);
+                prod_j0 = __shfl_sync(0xffffffffu, my_j0, prod_rbi);
+                bool all_valid = true;
+                int64_t first = -1;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = prod_i0 + r / NJ, j = prod_j0 + r % NJ;
+                    const int64_t ij = pair_index(i, j);
+                    prv[r] = (i < n) && (j <= i) && ij >= p.ij_begin && ij < p.ij_end;
+                    all_valid = all_valid && prv[r];
+                    int64_t off = 0;
+                    if (prv[r]) {
+                        off = (p.ioff[i] - p.shard_base) + (int64_t)j * subrow_offset(i) + subrow_offset(j);
+                        if (first < 0) first = off;
+                    }
+                    poff[r] = prv[r] ? (int)(off - first) : 0;
+                }
+                pbase = p.P + (first < 0 ? 0 : first) + l0;
+                prod_mode = (all_valid && prod_i0 >= k0 + JK_KN) ? (full_chunk ? 0 : 1) : 2;
+            }
+            const int k = k0 + prod_kk;
+            const double *src = pbase + subrow_offset(k);
+            const uint32_t dst = ring_u32 + stage_w * (RS * 512u);
+            if (prod_mode == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) cp_async16(dst + r * 512u, src + poff[r]);
+                cp_async16(dst + R * 512u, d2p + (size_t)prod_kk * ldd);
+            } else if (prod_mode == 1) {
+                const uint32_t nb = l0 <= k ? 16u : 0u;
+#pragma unroll
+                for (int r = 0; r < R; ++r) cp_async16_zfill(dst + r * 512u, src + poff[r], nb);
+                cp_async16_zfill(dst + R * 512u, d2p + (size_t)prod_kk * ldd, lane_in ? 16u : 0u);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = prod_i0 + r / NJ;
+                    const int lmax = !prv[r] ? -1 : (k < i ? k : (k == i ? prod_j0 + r % NJ : -1));
+                    cp_async16_zfill(dst + r * 512u, src + poff[r], l0 <= lmax ? 16u : 0u);
+                }
+                cp_async16_zfill(dst + R * 512u, d2p + (size_t)prod_kk * ldd, lane_in ? 16u : 0u);
+            }
+            stage_w = (stage_w + 1 == STAGES) ? 0 : stage_w + 1;
+            ++prod_it;
+            ++prod_kk;
+        };
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            if (prod_it < niter) issue_next();
+            cp_async_commit();
+        }
+
+        int cur_i0 = -1;
+        double2 accA[NS][NI], di[NS][NI];
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int a = 0; a < NI; ++a) accA[s][a] = di[s][a] = make_double2(0.0, 0.0);
+
+        auto flushA = [&]() {
+            if (WANTK && cur_i0 >= 0) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+#pragma unroll
+                    for (int a = 0; a < NI; ++a) {
+                        const bool ok = lane_in && (cur_i0 + a < n);
+                        double *dst = p.kt + s * nl + (size_t)(ok ? cur_i0 + a : 0) * ldd + (ok ? l0 : 0);
+                        red_add_if(ok, dst, accA[s][a].x);
+                        red_add_if(ok, dst + 1, accA[s][a].y);
+                    }
+            }
+        };
+
+        for (int rbi = 0; rbi < task.rb_count; ++rbi) {
+            const int i0 = __shfl_sync(0xffffffffu, my_i0, rbi), j0 = __shfl_sync(0xffffffffu, my_j0, rbi);
+            if (i0 != cur_i0) {
+                flushA();
+                cur_i0 = i0;
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+#pragma unroll
+                    for (int a = 0; a < NI; ++a) {
+                        accA[s][a] = make_double2(0.0, 0.0);
+                        if (WANTK)
+                            di[s][a] = (i0 + a < n && lane_in) ? ldg2(p.dsp + s * nl + (size_t)(i0 + a) * ldd + l0)
+                                                                : make_double2(0.0, 0.0);
+                    }
+            }
+            double2 dj[NS][NJ], accB[NS][NJ];
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int b = 0; b < NJ; ++b) {
+                    accB[s][b] = make_double2(0.0, 0.0);
+                    dj[s][b] = make_double2(0.0, 0.0);
+                    if (WANTK && j0 + b < n && lane_in) dj[s][b] = ldg2(p.dsp + s * nl + (size_t)(j0 + b) * ldd + l0);
+                }
+            double accJ[NI][NJ], d2ij[NI][NJ];
+#pragma unroll
+            for (int a = 0; a < NI; ++a)
+#pragma unroll
+                for (int b = 0; b < NJ; ++b) {
+                    const int i = i0 + a, j = j0 + b;
+                    const int64_t ij = pair_index(i, j);
+                    const bool rvalid = (i < n) && (j <= i) && ij >= p.ij_begin && ij < p.ij_end;
+                    accJ[a][b] = 0.0;
+                    d2ij[a][b] = rvalid ? __ldg(p.d2 + (size_t)i * ldd + j) : 0.0;
+                }
+            if (WANTK) {
+                // stage the warp-uniform operands: s_u[kk][q], q = s*(NI+NJ) + (a | NI+b); rows clamped into range
+                // (out-of-range rows only ever meet zero-filled integrals)
+                __syncwarp();
+                for (int e = lane; e < JK_KN * NV; e += 32) {
+                    const int kk = e / NV, q = e % NV, s = q / (NI + NJ), w = q % (NI + NJ);
+                    int row = w < NI ? i0 + w : j0 + (w - NI);
+                    row = row < n ? row : n - 1;
+                    const int k = (k0 + kk) < n ? (k0 + kk) : n - 1;
+                    s_u[kk * 8 + q] = __ldg(p.dsp + s * nl + (size_t)row * ldd + k);
+                }
+                __syncwarp();
+            }
+
+            for (int kk = kk_lo; kk < kk_hi; ++kk) {
+                const int k = k0 + kk;
+                if (prod_it < niter) issue_next();
+                cp_async_commit();
+                cp_async_wait<STAGES - 1>();  // this lane's 16 bytes of every row of the oldest stage have landed
+                const double2 *buf = ring + (size_t)stage_r * (RS * 32) + lane;
+                stage_r = (stage_r + 1 == STAGES) ? 0 : stage_r + 1;
+
+                double u[8];
+                if (WANTK) {
+                    const double2 *up = reinterpret_cast<const double2 *>(s_u + kk * 8);
+#pragma unroll
+                    for (int q = 0; q < (NV + 1) / 2; ++q) {
+                        const double2 w = up[q];
+                        u[2 * q] = w.x;
+                        u[2 * q + 1] = w.y;
+                    }
+                }
+                const double2 d2 = buf[R * 32];
+                double2 jt2 = make_double2(0.0, 0.0);
+                double cd[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) cd[q] = 0.0;
+#pragma unroll
+                for (int a = 0; a < NI; ++a)
+#pragma unroll
+                    for (int b = 0; b < NJ; ++b) {
+                        const double2 x = buf[(a * NJ + b) * 32];
+                        accJ[a][b] = fma(x.x, d2.x, fma(x.y, d2.y, accJ[a][b]));
+                        jt2.x = fma(x.x, d2ij[a][b], jt2.x);
+                        jt2.y = fma(x.y, d2ij[a][b], jt2.y);
+                        if (WANTK) {
+#pragma unroll
+                            for (int s = 0; s < NS; ++s) {
+                                const double ui = u[s * (NI + NJ) + a], uj = u[s * (NI + NJ) + NI + b];
+                                accA[s][a].x = fma(x.x, uj, accA[s][a].x);   // K~[i,l] += v D[j,k]
+                                accA[s][a].y = fma(x.y, uj, accA[s][a].y);
+                                accB[s][b].x = fma(x.x, ui, accB[s][b].x);   // K~[j,l] += v D[i,k]
+                                accB[s][b].y = fma(x.y, ui, accB[s][b].y);
+                                double &ca = cd[s * (NI + NJ) + a], &cb = cd[s * (NI + NJ) + NI + b];
+                                ca = fma(x.x, dj[s][b].x, fma(x.y, dj[s][b].y, ca));   // K~[i,k] += v D[j,l]
+                                cb = fma(x.x, di[s][a].x, fma(x.y, di[s][a].y, cb));   // K~[j,k] += v D[i,l]
+                            }
+                        }
+                    }
+                {
+                    double2 cur = s_jt[kk * 32 + lane];
+                    cur.x += jt2.x;
+                    cur.y += jt2.y;
+                    s_jt[kk * 32 + lane] = cur;
+                }
+                if (WANTK) {
+                    // cross-lane reduction of the NV partials through a conflict-free shared-memory transpose
+                    __syncwarp();
+                    double *wr = s_red + (lane >> 3) * 9 + (lane & 7);
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cd[q];
+                    __syncwarp();
+                    const int v = lane >> 2;
+                    const double *rd = s_red + v * JK_RED_STRIDE + (lane & 3) * 9;
+                    double sum = 0.0;
+                    if (v < NV) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) sum += rd[e];
+                    }
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    const int s = v / (NI + NJ), w = v % (NI + NJ);
+                    const int row = w < NI ? i0 + w : j0 + (w - NI);
+                    const bool ok = (lane & 3) == 0 && v < NV && row < n;
+                    red_add_if(ok, p.kt + (ok ? s * nl + (size_t)row * ldd + k : 0), sum);
+                }
+            }
+
+            if (WANTK) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+#pragma unroll
+                    for (int b = 0; b < NJ; ++b) {
+                        const bool ok = lane_in && (j0 + b < n);
+                        double *dst = p.kt + s * nl + (size_t)(ok ? j0 + b : 0) * ldd + (ok ? l0 : 0);
+                        red_add_if(ok, dst, accB[s][b].x);
+                        red_add_if(ok, dst + 1, accB[s][b].y);
+                    }
+            }
+            {
+                double jv[VJ];
+#pragma unroll
+                for (int q = 0; q < VJ; ++q) jv[q] = 0.0;
+#pragma unroll
+                for (int a = 0; a < NI; ++a)
+#pragma unroll
+                    for (int b = 0; b < NJ; ++b) jv[a * NJ + b] = accJ[a][b];
+                warp_reduce_multi<VJ>(jv, lane);
+                constexpr int GROUP = 32 / VJ;
+                const int g = lane / GROUP;
+                const int i = i0 + g / NJ, j = j0 + g % NJ;
+                const bool ok = (lane % GROUP) == 0 && g < NI * NJ && i < n && j <= i;  // rows outside the shard add 0
+                red_add_if(ok, p.jt + (ok ? (size_t)i * ldd + j : 0), jv[0]);
+            }
+        }
+        flushA();
+        if (lane_in) {
+            for (int kk = kk_lo; kk < kk_hi; ++kk) {
+                const int k = k0 + kk;
+                const double2 cur = s_jt[kk * 32 + lane];
+                if (l0 <= k) red_add(p.jt + (size_t)k * ldd + l0, cur.x);
+                if (l0 + 1 <= k) red_add(p.jt + (size_t)k * ldd + l0 + 1, cur.y);
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace sqcc

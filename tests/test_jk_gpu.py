@@ -46,12 +46,15 @@ def test_j_only_matches_oracle(engine, n):
     _check(engine, n, 77 + n, du, want_k=False)
 
 
-@pytest.mark.parametrize("n", [6, 36])
-def test_simple_variant_matches_oracle(engine, n):
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("n", [6, 36, 70])
+def test_other_kernel_variants_match_oracle(engine, n, variant):
+    """variant 1: simple atomics kernel; variant 2: tiled kernel with direct global loads (no TMA ring)."""
     d = synth.synth_density_rhf(n, max(1, n // 4), 1)
-    _check(engine, n, 5, d, variant=1)
+    _check(engine, n, 5, d, variant=variant)
     du = synth.synth_density_uhf(n, max(1, n // 3), max(1, n // 4), 2)
-    _check(engine, n, 5, du, variant=1)
+    _check(engine, n, 5, du, variant=variant)
+    _check(engine, n, 5, d, want_k=False, variant=variant)
 
 
 def test_reference_loop_form_small(engine):
