@@ -103,6 +103,7 @@ struct sqcc_ctx {
     int64_t shard_base = 0;       // offset of the shard's first row in the full native tensor
     sqcc::JKSchedule sched[2];    // [0]: NI=4,NJ=2 (nspin 1);  [1]: NI=2,NJ=2 (nspin 2)
     int jk_variant = 0;
+    int jk_cfg = 0;  // tuning knob of the pipelined kernel (warps, stages), see launch_pipe
 
     // J/K scratch
     double *d_dwork = nullptr;   // [3][N][ldd]: D2 = 2*(Da+Db), Da, Db (padded)

@@ -50,7 +50,7 @@ template <int NI, int NJ, int STAGES>
 constexpr int jk_pipe_warp_bytes()
 {
     // J~ slab + ring[STAGES][NI*NJ+1][512 B] + uniform-operand staging [KN][8] + reduction scratch [8][36]
-    return JK_KN * 32 * 16 + STAGES * (NI * NJ + 1) * 512 + JK_KN * 8 * 8 + 8 * JK_RED_STRIDE * 8;
+    return JK_KN * 32 * 16 + STAGES * (NI * NJ + 1) * 512 + JK_KN * 8 * 8 + 8 * JK_RED_STRIDE * 8 + 128;
 }
 
 template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES>
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
     constexpr int NS = WANTK ? NSPIN : 1;
     constexpr int NV = NS * (NI + NJ);  // lane-partial values reduced per sub-row
     static_assert(NV <= 8, "reduction scratch holds 8 values");
-    constexpr int VJ = next_pow2(NI * NJ);
+    static_assert(NI * NJ <= 8, "reduction scratch holds 8 values");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wbase = smem_raw + (size_t)warp * WARP_BYTES;
@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
     double2 *ring = s_jt + JK_KN * 32;                               // [STAGES][RS][32]
     double *s_u = reinterpret_cast<double *>(ring + STAGES * RS * 32);  // [KN][8]
     double *s_red = s_u + JK_KN * 8;                                 // [8][JK_RED_STRIDE]
+    double *s_w = s_red + 8 * JK_RED_STRIDE;                         // [8] D2[i_a, j_b] of the row-block
     const uint32_t ring_u32 = smem_u32(ring) + 16u * lane;
     const int n = p.n, ldd = p.ldd;
     const size_t nl = (size_t)n * ldd;
@@ -108,8 +109,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
         // ---- producer: this lane's 16 bytes of each row of the producer's row-block, one sub-row per call
         int prod_it = 0, prod_rbi = -1, prod_kk = kk_hi;  // forces a row-block load on the first issue
         int prod_i0 = 0, prod_j0 = 0, prod_mode = 2;      // 0: unmasked, 1: one mask (l0 <= k), 2: per-row masks
-        const double *pbase = p.P;
-        int poff[R];   // element offsets of the rows relative to pbase (fit 32 bits: rows of <= NI adjacent i)
+        const char *pbase = reinterpret_cast<const char *>(p.P);   // running byte pointer: first valid row, sub-row k
+        const char *d2row = reinterpret_cast<const char *>(d2p);   // running byte pointer into the D2 tile
+        unsigned int poff[R];  // BYTE offsets of the rows relative to pbase (< 4 GB: rows of <= NI adjacent i)
         bool prv[R];
         auto issue_next = [&]() {
             if (prod_kk == kk_hi) {  // advance to the next row-block
@@ -130,32 +132,34 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                         off = (p.ioff[i] - p.shard_base) + (int64_t)j * subrow_offset(i) + subrow_offset(j);
                         if (first < 0) first = off;
                     }
-                    poff[r] = prv[r] ? (int)(off - first) : 0;
+                    poff[r] = prv[r] ? (unsigned int)((off - first) * 8) : 0u;
                 }
-                pbase = p.P + (first < 0 ? 0 : first) + l0;
+                pbase = reinterpret_cast<const char *>(p.P + (first < 0 ? 0 : first) + l0 + subrow_offset(k0 + kk_lo));
+                d2row = reinterpret_cast<const char *>(d2p + (size_t)kk_lo * ldd);
                 prod_mode = (all_valid && prod_i0 >= k0 + JK_KN) ? (full_chunk ? 0 : 1) : 2;
             }
             const int k = k0 + prod_kk;
-            const double *src = pbase + subrow_offset(k);
             const uint32_t dst = ring_u32 + stage_w * (RS * 512u);
             if (prod_mode == 0) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) cp_async16(dst + r * 512u, src + poff[r]);
-                cp_async16(dst + R * 512u, d2p + (size_t)prod_kk * ldd);
+                for (int r = 0; r < R; ++r) cp_async16(dst + r * 512u, pbase + poff[r]);
+                cp_async16(dst + R * 512u, d2row);
             } else if (prod_mode == 1) {
                 const uint32_t nb = l0 <= k ? 16u : 0u;
 #pragma unroll
-                for (int r = 0; r < R; ++r) cp_async16_zfill(dst + r * 512u, src + poff[r], nb);
-                cp_async16_zfill(dst + R * 512u, d2p + (size_t)prod_kk * ldd, lane_in ? 16u : 0u);
+                for (int r = 0; r < R; ++r) cp_async16_zfill(dst + r * 512u, pbase + poff[r], nb);
+                cp_async16_zfill(dst + R * 512u, d2row, lane_in ? 16u : 0u);
             } else {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int i = prod_i0 + r / NJ;
                     const int lmax = !prv[r] ? -1 : (k < i ? k : (k == i ? prod_j0 + r % NJ : -1));
-                    cp_async16_zfill(dst + r * 512u, src + poff[r], l0 <= lmax ? 16u : 0u);
+                    cp_async16_zfill(dst + r * 512u, pbase + poff[r], l0 <= lmax ? 16u : 0u);
                 }
-                cp_async16_zfill(dst + R * 512u, d2p + (size_t)prod_kk * ldd, lane_in ? 16u : 0u);
+                cp_async16_zfill(dst + R * 512u, d2row, lane_in ? 16u : 0u);
             }
+            pbase += (size_t)pad_even(k + 1) * 8;   // next sub-row of every row
+            d2row += (size_t)ldd * 8;
             stage_w = (stage_w + 1 == STAGES) ? 0 : stage_w + 1;
             ++prod_it;
             ++prod_kk;
@@ -211,30 +215,54 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                     dj[s][b] = make_double2(0.0, 0.0);
                     if (WANTK && j0 + b < n && lane_in) dj[s][b] = ldg2(p.dsp + s * nl + (size_t)(j0 + b) * ldd + l0);
                 }
-            double accJ[NI][NJ], d2ij[NI][NJ];
+            double accJ[NI][NJ];
 #pragma unroll
             for (int a = 0; a < NI; ++a)
 #pragma unroll
-                for (int b = 0; b < NJ; ++b) {
-                    const int i = i0 + a, j = j0 + b;
-                    const int64_t ij = pair_index(i, j);
-                    const bool rvalid = (i < n) && (j <= i) && ij >= p.ij_begin && ij < p.ij_end;
-                    accJ[a][b] = 0.0;
-                    d2ij[a][b] = rvalid ? __ldg(p.d2 + (size_t)i * ldd + j) : 0.0;
-                }
-            if (WANTK) {
-                // stage the warp-uniform operands: s_u[kk][q], q = s*(NI+NJ) + (a | NI+b); rows clamped into range
-                // (out-of-range rows only ever meet zero-filled integrals)
-                __syncwarp();
-                for (int e = lane; e < JK_KN * NV; e += 32) {
-                    const int kk = e / NV, q = e % NV, s = q / (NI + NJ), w = q % (NI + NJ);
+                for (int b = 0; b < NJ; ++b) accJ[a][b] = 0.0;
+            // stage the warp-uniform operands of this row-block in shared memory:
+            //   s_w[r]      = D2[i_a, j_b] (0 for rows that are not in the shard)
+            //   s_u[kk][q]  = D_s[row_q, k0+kk], q = s*(NI+NJ) + (a | NI+b); rows/k clamped into range
+            //                 (out-of-range operands only ever meet zero-filled integrals)
+            __syncwarp();
+            if (lane < R) {
+                const int i = i0 + lane / NJ, j = j0 + lane % NJ;
+                const int64_t ij = pair_index(i, j);
+                const bool rvalid = (i < n) && (j <= i) && ij >= p.ij_begin && ij < p.ij_end;
+                s_w[lane] = rvalid ? __ldg(p.d2 + (size_t)i * ldd + j) : 0.0;
+            }
+            if (WANTK && lane < JK_KN) {
+                const int k = (k0 + lane) < n ? (k0 + lane) : n - 1;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const int s = q / (NI + NJ), w = q % (NI + NJ);
                     int row = w < NI ? i0 + w : j0 + (w - NI);
                     row = row < n ? row : n - 1;
-                    const int k = (k0 + kk) < n ? (k0 + kk) : n - 1;
-                    s_u[kk * 8 + q] = __ldg(p.dsp + s * nl + (size_t)row * ldd + k);
+                    s_u[lane * 8 + q] = __ldg(p.dsp + s * nl + (size_t)row * ldd + k);
                 }
-                __syncwarp();
             }
+            __syncwarp();
+
+            // The cross-lane reduction of the K~[.,k] partials of sub-row k is deferred by one iteration: the
+            // partials are written to the transpose scratch at the end of iteration k, read back at the top of
+            // iteration k+1 and summed / flushed after that iteration's FMA block has been issued.
+            const int red_v = lane >> 2;   // value this lane sums (4 lanes per value, 8 scratch entries each)
+            const double *red_rd = s_red + red_v * JK_RED_STRIDE + (lane & 3) * 9;
+            double *red_wr = s_red + (lane >> 3) * 9 + (lane & 7);
+            double *red_dst = p.kt;
+            bool red_ok = false;
+            if (WANTK) {
+                const int s = red_v / (NI + NJ), w = red_v % (NI + NJ);
+                const int row = w < NI ? i0 + w : j0 + (w - NI);
+                red_ok = (lane & 3) == 0 && red_v < NV && row < n;
+                if (red_ok) red_dst = p.kt + s * nl + (size_t)row * ldd;
+            }
+            auto red_finish = [&](const double (&r8)[8], int k) {
+                double sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                red_add_if(red_ok, red_dst + (red_ok ? k : 0), sum);
+            };
 
             for (int kk = kk_lo; kk < kk_hi; ++kk) {
                 const int k = k0 + kk;
@@ -265,8 +293,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                     for (int b = 0; b < NJ; ++b) {
                         const double2 x = buf[(a * NJ + b) * 32];
                         accJ[a][b] = fma(x.x, d2.x, fma(x.y, d2.y, accJ[a][b]));
-                        jt2.x = fma(x.x, d2ij[a][b], jt2.x);
-                        jt2.y = fma(x.y, d2ij[a][b], jt2.y);
+                        const double wij = s_w[a * NJ + b];
+                        jt2.x = fma(x.x, wij, jt2.x);
+                        jt2.y = fma(x.y, wij, jt2.y);
                         if (WANTK) {
 #pragma unroll
                             for (int s = 0; s < NS; ++s) {
@@ -288,26 +317,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                     s_jt[kk * 32 + lane] = cur;
                 }
                 if (WANTK) {
-                    // cross-lane reduction of the NV partials through a conflict-free shared-memory transpose
-                    __syncwarp();
-                    double *wr = s_red + (lane >> 3) * 9 + (lane & 7);
+                    if (kk > kk_lo) {   // previous sub-row's partials: written one iteration ago, so no store->load stall
+                        double r8[8];
 #pragma unroll
-                    for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cd[q];
-                    __syncwarp();
-                    const int v = lane >> 2;
-                    const double *rd = s_red + v * JK_RED_STRIDE + (lane & 3) * 9;
-                    double sum = 0.0;
-                    if (v < NV) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) sum += rd[e];
+                        for (int e = 0; e < 8; ++e) r8[e] = (red_v < NV) ? red_rd[e] : 0.0;
+                        red_finish(r8, k - 1);
                     }
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                    const int s = v / (NI + NJ), w = v % (NI + NJ);
-                    const int row = w < NI ? i0 + w : j0 + (w - NI);
-                    const bool ok = (lane & 3) == 0 && v < NV && row < n;
-                    red_add_if(ok, p.kt + (ok ? s * nl + (size_t)row * ldd + k : 0), sum);
+                    // publish this sub-row's NV lane partials (conflict-free shared-memory transpose)
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) red_wr[q * JK_RED_STRIDE] = cd[q];
+                    __syncwarp();
                 }
+            }
+            if (WANTK) {   // last sub-row of the sweep
+                double r8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r8[e] = (red_v < NV) ? red_rd[e] : 0.0;
+                red_finish(r8, k0 + kk_hi - 1);
             }
 
             if (WANTK) {
@@ -322,19 +349,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                     }
             }
             {
-                double jv[VJ];
-#pragma unroll
-                for (int q = 0; q < VJ; ++q) jv[q] = 0.0;
+                // J~[i_a, j_b]: reduce the R row dots across the warp (same shared-memory transpose)
+                __syncwarp();
+                double *wr = s_red + (lane >> 3) * 9 + (lane & 7);
 #pragma unroll
                 for (int a = 0; a < NI; ++a)
 #pragma unroll
-                    for (int b = 0; b < NJ; ++b) jv[a * NJ + b] = accJ[a][b];
-                warp_reduce_multi<VJ>(jv, lane);
-                constexpr int GROUP = 32 / VJ;
-                const int g = lane / GROUP;
-                const int i = i0 + g / NJ, j = j0 + g % NJ;
-                const bool ok = (lane % GROUP) == 0 && g < NI * NJ && i < n && j <= i;  // rows outside the shard add 0
-                red_add_if(ok, p.jt + (ok ? (size_t)i * ldd + j : 0), jv[0]);
+                    for (int b = 0; b < NJ; ++b) wr[(a * NJ + b) * JK_RED_STRIDE] = accJ[a][b];
+                __syncwarp();
+                const int v = lane >> 2;
+                const double *rd = s_red + v * JK_RED_STRIDE + (lane & 3) * 9;
+                double sum = 0.0;
+                if (v < R) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) sum += rd[e];
+                }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                const int i = i0 + v / NJ, j = j0 + v % NJ;
+                const bool ok = (lane & 3) == 0 && v < R && i < n && j <= i;  // rows outside the shard add 0
+                red_add_if(ok, p.jt + (ok ? (size_t)i * ldd + j : 0), sum);
             }
         }
         flushA();
