@@ -46,19 +46,21 @@ __device__ __forceinline__ void red_add_if(bool pred, double *ptr, double v)
 
 constexpr int JK_RED_STRIDE = 36;  // value stride of the reduction scratch (== 4 mod 16, >= 3*9+8)
 
-template <int NI, int NJ, int STAGES>
+template <int NI, int NJ, int STAGES, bool SLAB>
 constexpr int jk_pipe_warp_bytes()
 {
     // J~ slab + ring[STAGES][NI*NJ+1][512 B] + uniform-operand staging [KN][8] + reduction scratch [8][36]
-    return JK_KN * 32 * 16 + STAGES * (NI * NJ + 1) * 512 + JK_KN * 8 * 8 + 8 * JK_RED_STRIDE * 8 + 128;
+    return (SLAB ? JK_KN * 32 * 16 : 0) + STAGES * (NI * NJ + 1) * 512 + JK_KN * 8 * 8 + 8 * JK_RED_STRIDE * 8 + 128;
 }
 
-template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES>
+// SLAB = true : J~[k, l-chunk] is accumulated over all row-blocks of a task in a warp-private shared-memory slab;
+// SLAB = false: it is flushed every sub-row with red.global.add.f64 (no slab: more warps / ring stages fit).
+template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES, bool SLAB>
 __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p)
 {
     constexpr int R = NI * NJ;
     constexpr int RS = R + 1;  // ring rows per stage: R ERI rows + the D2 tile row
-    constexpr int WARP_BYTES = jk_pipe_warp_bytes<NI, NJ, STAGES>();
+    constexpr int WARP_BYTES = jk_pipe_warp_bytes<NI, NJ, STAGES, SLAB>();
     constexpr int NS = WANTK ? NSPIN : 1;
     constexpr int NV = NS * (NI + NJ);  // lane-partial values reduced per sub-row
     static_assert(NV <= 8, "reduction scratch holds 8 values");
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wbase = smem_raw + (size_t)warp * WARP_BYTES;
     double2 *s_jt = reinterpret_cast<double2 *>(wbase);              // [KN][32]
-    double2 *ring = s_jt + JK_KN * 32;                               // [STAGES][RS][32]
+    double2 *ring = s_jt + (SLAB ? JK_KN * 32 : 0);                               // [STAGES][RS][32]
     double *s_u = reinterpret_cast<double *>(ring + STAGES * RS * 32);  // [KN][8]
     double *s_red = s_u + JK_KN * 8;                                 // [8][JK_RED_STRIDE]
     double *s_w = s_red + 8 * JK_RED_STRIDE;                         // [8] D2[i_a, j_b] of the row-block
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
         const int niter = task.rb_count * nkk;
 
 #pragma unroll 4
-        for (int kk = 0; kk < JK_KN; ++kk) s_jt[kk * 32 + lane] = make_double2(0.0, 0.0);
+        for (int kk = 0; kk < (SLAB ? JK_KN : 0); ++kk) s_jt[kk * 32 + lane] = make_double2(0.0, 0.0);
 
         // row-block list of the task, one entry per lane (rb_count <= 32)
         int my_i0 = 0, my_j0 = 0;
@@ -310,11 +312,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                             }
                         }
                     }
-                {
+                if (SLAB) {
                     double2 cur = s_jt[kk * 32 + lane];
                     cur.x += jt2.x;
                     cur.y += jt2.y;
                     s_jt[kk * 32 + lane] = cur;
+                } else {
+                    const bool ok = lane_in && l0 <= k;
+                    double *dst = p.jt + (ok ? (size_t)k * ldd + l0 : 0);
+                    red_add_if(ok, dst, jt2.x);
+                    red_add_if(ok && l0 + 1 <= k, dst + 1, jt2.y);
                 }
                 if (WANTK) {
                     if (kk > kk_lo) {   // previous sub-row's partials: written one iteration ago, so no store->load stall
@@ -372,7 +379,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
             }
         }
         flushA();
-        if (lane_in) {
+        if (SLAB && lane_in) {
             for (int kk = kk_lo; kk < kk_hi; ++kk) {
                 const int k = k0 + kk;
                 const double2 cur = s_jt[kk * 32 + lane];
