@@ -215,10 +215,15 @@ class SGaussInterface:
     def compute_external_potential_integrals(self, mm_coords, mm_charges, real_space_grids, weights_grids):
         """Grid quadrature of the MM point-charge potential, form of interface_psi4.py:387-403."""
         phi = self.generate_ao_values_at_grids(real_space_grids)
+        v = self.mm_potential_at_grids(mm_coords, mm_charges, real_space_grids)
+        return phi.T @ (phi * (weights_grids * v)[:, None])
+
+    def mm_potential_at_grids(self, mm_coords, mm_charges, real_space_grids):
         v = np.zeros(len(real_space_grids))
         for xyz, q in zip(np.asarray(mm_coords) * ANG_TO_BOHR, mm_charges):
-            v += -q / np.maximum(np.linalg.norm(real_space_grids - xyz, axis=-1), 1e-10)
-        return phi.T @ (phi * (weights_grids * v)[:, None])
+            r = np.linalg.norm(real_space_grids - xyz, axis=-1)
+            v += np.where(r > 1e-10, -q / np.where(r > 1e-10, r, 1.0), 0.0)
+        return v
 
 
 def stub_module(name="interface_psi4"):
