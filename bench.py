@@ -11,7 +11,7 @@ partial [J; K] is summed with one NCCL all-reduce.  A "step" is one Fock build.
 
   value        builds/s, density and outputs resident in HBM (device pointers), CUDA-event timed, max over ranks
   e2e          builds/s through the host-buffer API (numpy D in, numpy J/K out; H2D + D2H inside the timed region)
-  roofline     dominant kernel (jk_tiled_kernel): algorithmic bytes 8*nquad(shard) / CUDA-event kernel time
+  roofline     dominant kernel (jk_pipe_kernel): algorithmic bytes 8*nquad(shard) / CUDA-event kernel time
   cpu_baseline the oracle's multi-core C port of the same pass, timed on a bounded row sample of the same tensor
 """
 import argparse
@@ -272,7 +272,7 @@ def main():
             "eri_gbs_aggregate": nquad(n) * 8 / (ms_per_step * 1e-3) / 1e9,
             "frac_of_8tbs_per_gpu": nquad(n) * 8 / (ms_per_step * 1e-3) / 1e9 / world / 8000.0,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "jk_tiled_kernel", "kernel_ms": float(kt.item()),
+                         "traffic": None, "kernel": "jk_pipe_kernel", "kernel_ms": float(kt.item()),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": float(ab.item())},
             "e2e": {"value": e2e_builds, "unit": "builds/s", "h2d_bytes_per_step": int(d_host.nbytes),
                     "d2h_bytes_per_step": int(2 * n * n * 8)},
