@@ -7,8 +7,8 @@ canonical  (SURVEY.md A.1): pair index ``ij = i(i+1)/2 + j`` (i >= j), quads ``i
            ``interface_psi4.py:177-190`` (``ERI[i,j,k,l]``).
 
 native v1  (what the CUDA kernels stream): same rows ``ij`` in the same order; inside a row the
-           sub-row for ``k`` (l = 0..k, or l = 0..j when k == i) is padded to an EVEN number of
-           doubles so that every sub-row starts 16-byte aligned (128-bit loads).  Pad cells are 0.0.
+           sub-row for ``k`` (l = 0..k, or l = 0..j when k == i) is padded to a multiple of 16
+           doubles so that every sub-row starts 128-byte aligned (one L1 line per 8-lane quarter of a 128-bit load).  Pad cells are 0.0.
            Stored value is (ij|kl) * f with the degeneracy factor
            f = 0.5^[i==j] * 0.5^[k==l] * 0.5^[ij==kl]   (exact powers of two).
 """
@@ -65,20 +65,23 @@ def unpack_canonical(packed, n):
 
 
 # ---------------------------------------------------------------- native v1 layout
-def pad_even(x):
-    return x + (x & 1)
+LAYOUT_ALIGN = 16  # doubles; must equal SUBROW_ALIGN in sqcc_b200/csrc/common.cuh
+
+
+def pad_sub(x):
+    return (x + (LAYOUT_ALIGN - 1)) // LAYOUT_ALIGN * LAYOUT_ALIGN
 
 
 def subrow_offset(k):
-    """Te(k): offset (in doubles) of sub-row k inside any row.  Te(2m)=2m(m+1), Te(2m+1)=2(m+1)^2."""
+    """Te(k) = sum_{k' < k} pad_sub(k' + 1) = A (M + 1) (A M / 2 + r), A = LAYOUT_ALIGN, M = k // A, r = k % A."""
     k = np.asarray(k, dtype=np.int64)
-    m = k // 2
-    return np.where(k % 2 == 0, 2 * m * (m + 1), 2 * (m + 1) * (m + 1))
+    m, r = k // LAYOUT_ALIGN, k % LAYOUT_ALIGN
+    return LAYOUT_ALIGN * (m + 1) * ((LAYOUT_ALIGN // 2) * m + r)
 
 
 def row_length(i, j):
     """Padded length (doubles) of row (i, j): sub-rows k < i are full, sub-row k == i holds l <= j."""
-    return subrow_offset(i) + pad_even(np.asarray(j, dtype=np.int64) + 1)
+    return subrow_offset(i) + pad_sub(np.asarray(j, dtype=np.int64) + 1)
 
 
 def row_offsets(n, ij_begin=0, ij_end=None):

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(double *__restrict__ P, 
                 }
                 sub[l] = v * degeneracy(i, j, k, l);
             }
-            if (lane == 0 && ((lmax + 1) & 1)) sub[lmax + 1] = 0.0;  // pad cell
+            for (int l = lmax + 1 + lane; l < (int)pad_sub(lmax + 1); l += 32) sub[l] = 0.0;  // pad cells
         }
     }
 }

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_tiled_kernel(const JKParams 
                                 v[a][b] = ldg_stream(rp[a][b] + te);
                             }
                         }
-                    te += pad_even(k + 1);
+                    te += pad_sub(k + 1);
                     const double2 d2 = s_d2[kk * 32 + lane];
                     double2 jt2 = make_double2(0.0, 0.0);
                     double cd[VCD];
@@ -484,7 +484,7 @@ int jk_build_schedule(sqcc_ctx *ctx)
     return SQCC_OK;
 }
 
-template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES, bool SLAB>
+template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES, bool SLAB, bool RING>
 static int launch_pipe_cfg(sqcc_ctx *ctx, const JKParams &p);
 
 // (WARPS, STAGES) of the pipelined kernel: tuning knob jk_cfg (0 = default).
@@ -492,18 +492,18 @@ template <int NI, int NJ, int NSPIN, bool WANTK>
 static int launch_pipe(sqcc_ctx *ctx, const JKParams &p)
 {
     switch (ctx->jk_cfg) {
-    case 1: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 12, 3, false>(ctx, p);
-    case 2: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 8, 3, true>(ctx, p);
-    case 3: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 12, 2, false>(ctx, p);
-    default: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 11, 2, true>(ctx, p);
+    case 1: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 12, 3, false, true>(ctx, p);
+    case 2: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 8, 3, true, true>(ctx, p);
+    case 3: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 8, 1, true, false>(ctx, p);
+    default: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 11, 2, true, true>(ctx, p);
     }
 }
 
-template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES, bool SLAB>
+template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES, bool SLAB, bool RING>
 static int launch_pipe_cfg(sqcc_ctx *ctx, const JKParams &p)
 {
-    const size_t smem = (size_t)WARPS * jk_pipe_warp_bytes<NI, NJ, STAGES, SLAB>();
-    auto kern = jk_pipe_kernel<NI, NJ, NSPIN, WANTK, WARPS, STAGES, SLAB>;
+    const size_t smem = (size_t)WARPS * jk_pipe_warp_bytes<NI, NJ, STAGES, SLAB, RING>();
+    auto kern = jk_pipe_kernel<NI, NJ, NSPIN, WANTK, WARPS, STAGES, SLAB, RING>;
     SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SQCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));

@@ -46,21 +46,25 @@ __device__ __forceinline__ void red_add_if(bool pred, double *ptr, double v)
 
 constexpr int JK_RED_STRIDE = 36;  // value stride of the reduction scratch (== 4 mod 16, >= 3*9+8)
 
-template <int NI, int NJ, int STAGES, bool SLAB>
+template <int NI, int NJ, int STAGES, bool SLAB, bool RING>
 constexpr int jk_pipe_warp_bytes()
 {
-    // J~ slab + ring[STAGES][NI*NJ+1][512 B] + uniform-operand staging [KN][8] + reduction scratch [8][36]
-    return (SLAB ? JK_KN * 32 * 16 : 0) + STAGES * (NI * NJ + 1) * 512 + JK_KN * 8 * 8 + 8 * JK_RED_STRIDE * 8 + 128;
+    // J~ slab + (ring[STAGES][NI*NJ+1][512 B] | D2 tile slab) + uniform-operand staging [KN][8] + reduction scratch
+    return (SLAB ? JK_KN * 32 * 16 : 0) + (RING ? STAGES * (NI * NJ + 1) * 512 : JK_KN * 32 * 16) + JK_KN * 8 * 8 +
+           8 * JK_RED_STRIDE * 8 + 128;
 }
 
 // SLAB = true : J~[k, l-chunk] is accumulated over all row-blocks of a task in a warp-private shared-memory slab;
 // SLAB = false: it is flushed every sub-row with red.global.add.f64 (no slab: more warps / ring stages fit).
-template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES, bool SLAB>
+// RING = true : ERI stream staged through the shared-memory cp.async ring (STAGES deep);
+// RING = false: ERI stream loaded straight into registers with 128-bit ld.global.nc, one sub-row ahead of the FMA
+//               block (no shared-memory traffic for the stream; the D2 tile is staged once per task in a slab).
+template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES, bool SLAB, bool RING>
 __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p)
 {
     constexpr int R = NI * NJ;
     constexpr int RS = R + 1;  // ring rows per stage: R ERI rows + the D2 tile row
-    constexpr int WARP_BYTES = jk_pipe_warp_bytes<NI, NJ, STAGES, SLAB>();
+    constexpr int WARP_BYTES = jk_pipe_warp_bytes<NI, NJ, STAGES, SLAB, RING>();
     constexpr int NS = WANTK ? NSPIN : 1;
     constexpr int NV = NS * (NI + NJ);  // lane-partial values reduced per sub-row
     static_assert(NV <= 8, "reduction scratch holds 8 values");
@@ -70,7 +74,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
     unsigned char *wbase = smem_raw + (size_t)warp * WARP_BYTES;
     double2 *s_jt = reinterpret_cast<double2 *>(wbase);              // [KN][32]
     double2 *ring = s_jt + (SLAB ? JK_KN * 32 : 0);                               // [STAGES][RS][32]
-    double *s_u = reinterpret_cast<double *>(ring + STAGES * RS * 32);  // [KN][8]
+    double2 *s_d2 = ring;                                            // [KN][32] (RING == false only)
+    double *s_u = reinterpret_cast<double *>(ring + (RING ? STAGES * RS * 32 : JK_KN * 32));  // [KN][8]
     double *s_red = s_u + JK_KN * 8;                                 // [8][JK_RED_STRIDE]
     double *s_w = s_red + 8 * JK_RED_STRIDE;                         // [8] D2[i_a, j_b] of the row-block
     const uint32_t ring_u32 = smem_u32(ring) + 16u * lane;
@@ -115,6 +120,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
         const char *d2row = reinterpret_cast<const char *>(d2p);   // running byte pointer into the D2 tile
         unsigned int poff[R];  // BYTE offsets of the rows relative to pbase (< 4 GB: rows of <= NI adjacent i)
         bool prv[R];
+        double2 xn[R];         // RING == false: the next sub-row's integrals, in flight during the current FMA block
         auto issue_next = [&]() {
             if (prod_kk == kk_hi) {  // advance to the next row-block
                 prod_kk = kk_lo;
@@ -142,7 +148,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
             }
             const int k = k0 + prod_kk;
             const uint32_t dst = ring_u32 + stage_w * (RS * 512u);
-            if (prod_mode == 0) {
+            if (!RING) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    bool on = true;
+                    if (prod_mode == 1) on = l0 <= k;
+                    if (prod_mode == 2) {
+                        const int i = prod_i0 + r / NJ;
+                        const int lmax = !prv[r] ? -1 : (k < i ? k : (k == i ? prod_j0 + r % NJ : -1));
+                        on = l0 <= lmax;
+                    }
+                    xn[r] = on ? ldg_stream(reinterpret_cast<const double *>(pbase + poff[r])) : make_double2(0.0, 0.0);
+                }
+            } else if (prod_mode == 0) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) cp_async16(dst + r * 512u, pbase + poff[r]);
                 cp_async16(dst + R * 512u, d2row);
@@ -160,16 +178,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                 }
                 cp_async16_zfill(dst + R * 512u, d2row, lane_in ? 16u : 0u);
             }
-            pbase += (size_t)pad_even(k + 1) * 8;   // next sub-row of every row
+            pbase += (size_t)pad_sub(k + 1) * 8;   // next sub-row of every row
             d2row += (size_t)ldd * 8;
             stage_w = (stage_w + 1 == STAGES) ? 0 : stage_w + 1;
             ++prod_it;
             ++prod_kk;
         };
+        if (RING) {
 #pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s) {
-            if (prod_it < niter) issue_next();
-            cp_async_commit();
+            for (int s = 0; s < STAGES - 1; ++s) {
+                if (prod_it < niter) issue_next();
+                cp_async_commit();
+            }
+        } else {
+            __syncwarp();  // previous task's tile reads are done
+#pragma unroll 4
+            for (int kk = 0; kk < JK_KN; ++kk)
+                s_d2[kk * 32 + lane] = (k0 + kk < n && lane_in) ? ldg2(p.d2 + (size_t)(k0 + kk) * ldd + l0) : make_double2(0.0, 0.0);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) xn[r] = make_double2(0.0, 0.0);
+            issue_next();
         }
 
         int cur_i0 = -1;
@@ -268,11 +297,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
 
             for (int kk = kk_lo; kk < kk_hi; ++kk) {
                 const int k = k0 + kk;
-                if (prod_it < niter) issue_next();
-                cp_async_commit();
-                cp_async_wait<STAGES - 1>();  // this lane's 16 bytes of every row of the oldest stage have landed
+                double2 xc[R];
                 const double2 *buf = ring + (size_t)stage_r * (RS * 32) + lane;
-                stage_r = (stage_r + 1 == STAGES) ? 0 : stage_r + 1;
+                if (RING) {
+                    if (prod_it < niter) issue_next();
+                    cp_async_commit();
+                    cp_async_wait<STAGES - 1>();  // this lane's 16 bytes of every row of the oldest stage have landed
+                    stage_r = (stage_r + 1 == STAGES) ? 0 : stage_r + 1;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) xc[r] = xn[r];
+                    if (prod_it < niter) issue_next();   // next sub-row's loads fly during this FMA block
+                }
 
                 double u[8];
                 if (WANTK) {
@@ -284,7 +320,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                         u[2 * q + 1] = w.y;
                     }
                 }
-                const double2 d2 = buf[R * 32];
+                const double2 d2 = RING ? buf[R * 32] : s_d2[kk * 32 + lane];
                 double2 jt2 = make_double2(0.0, 0.0);
                 double cd[8];
 #pragma unroll
@@ -293,7 +329,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                 for (int a = 0; a < NI; ++a)
 #pragma unroll
                     for (int b = 0; b < NJ; ++b) {
-                        const double2 x = buf[(a * NJ + b) * 32];
+                        const double2 x = RING ? buf[(a * NJ + b) * 32] : xc[a * NJ + b];
                         accJ[a][b] = fma(x.x, d2.x, fma(x.y, d2.y, accJ[a][b]));
                         const double wij = s_w[a * NJ + b];
                         jt2.x = fma(x.x, wij, jt2.x);
@@ -388,7 +424,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
             }
         }
     }
-    cp_async_wait<0>();
+    if (RING) cp_async_wait<0>();
 }
 
 }  // namespace sqcc
