@@ -44,7 +44,7 @@ __device__ __forceinline__ void red_add_if(bool pred, double *ptr, double v)
         : "memory");
 }
 
-constexpr int JK_RED_STRIDE = 36;  // value stride of the reduction scratch (== 4 mod 16, >= 3*9+8)
+constexpr int JK_RED_STRIDE = 17;  // value stride of the reduction scratch (odd: conflict-free 4x4 read pattern)
 
 template <int NI, int NJ, int STAGES, bool SLAB, bool RING>
 constexpr int jk_pipe_warp_bytes()
@@ -277,9 +277,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
             // The cross-lane reduction of the K~[.,k] partials of sub-row k is deferred by one iteration: the
             // partials are written to the transpose scratch at the end of iteration k, read back at the top of
             // iteration k+1 and summed / flushed after that iteration's FMA block has been issued.
-            const int red_v = lane >> 2;   // value this lane sums (4 lanes per value, 8 scratch entries each)
-            const double *red_rd = s_red + red_v * JK_RED_STRIDE + (lane & 3) * 9;
-            double *red_wr = s_red + (lane >> 3) * 9 + (lane & 7);
+            // Reduction scheme: one xor-16 shuffle halves the partials to 16 lanes, which store them (1 wavefront per
+            // value); lane t then sums 4 entries of value t>>2 (stride 17: the 4x4 read pattern of a half-warp is
+            // conflict free) and two more shuffles finish the sum.
+            const int red_v = lane >> 2;   // value this lane sums (4 lanes per value, 4 scratch entries each)
+            const double *red_rd = s_red + red_v * JK_RED_STRIDE + (lane & 3) * 4;
+            double *red_wr = s_red + (lane & 15);
             double *red_dst = p.kt;
             bool red_ok = false;
             if (WANTK) {
@@ -288,8 +291,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                 red_ok = (lane & 3) == 0 && red_v < NV && row < n;
                 if (red_ok) red_dst = p.kt + s * nl + (size_t)row * ldd;
             }
-            auto red_finish = [&](const double (&r8)[8], int k) {
-                double sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+            auto red_finish = [&](const double (&r4)[4], int k) {
+                double sum = (r4[0] + r4[1]) + (r4[2] + r4[3]);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 2);
                 red_add_if(red_ok, red_dst + (red_ok ? k : 0), sum);
@@ -331,7 +334,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                     for (int b = 0; b < NJ; ++b) {
                         const double2 x = RING ? buf[(a * NJ + b) * 32] : xc[a * NJ + b];
                         accJ[a][b] = fma(x.x, d2.x, fma(x.y, d2.y, accJ[a][b]));
-                        const double wij = s_w[a * NJ + b];
+                        const double2 w2 = reinterpret_cast<const double2 *>(s_w)[(a * NJ + b) >> 1];
+                        const double wij = ((a * NJ + b) & 1) ? w2.y : w2.x;
                         jt2.x = fma(x.x, wij, jt2.x);
                         jt2.y = fma(x.y, wij, jt2.y);
                         if (WANTK) {
@@ -361,23 +365,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                 }
                 if (WANTK) {
                     if (kk > kk_lo) {   // previous sub-row's partials: written one iteration ago, so no store->load stall
-                        double r8[8];
+                        double r4[4];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) r8[e] = (red_v < NV) ? red_rd[e] : 0.0;
-                        red_finish(r8, k - 1);
+                        for (int e = 0; e < 4; ++e) r4[e] = (red_v < NV) ? red_rd[e] : 0.0;
+                        red_finish(r4, k - 1);
                     }
                     // publish this sub-row's NV lane partials (conflict-free shared-memory transpose)
-                    __syncwarp();
 #pragma unroll
-                    for (int q = 0; q < NV; ++q) red_wr[q * JK_RED_STRIDE] = cd[q];
+                    for (int q = 0; q < NV; ++q) cd[q] += __shfl_xor_sync(0xffffffffu, cd[q], 16);
+                    __syncwarp();
+                    if (lane < 16) {
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) red_wr[q * JK_RED_STRIDE] = cd[q];
+                    }
                     __syncwarp();
                 }
             }
             if (WANTK) {   // last sub-row of the sweep
-                double r8[8];
+                double r4[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) r8[e] = (red_v < NV) ? red_rd[e] : 0.0;
-                red_finish(r8, k0 + kk_hi - 1);
+                for (int e = 0; e < 4; ++e) r4[e] = (red_v < NV) ? red_rd[e] : 0.0;
+                red_finish(r4, k0 + kk_hi - 1);
             }
 
             if (WANTK) {
@@ -393,19 +401,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
             }
             {
                 // J~[i_a, j_b]: reduce the R row dots across the warp (same shared-memory transpose)
-                __syncwarp();
-                double *wr = s_red + (lane >> 3) * 9 + (lane & 7);
 #pragma unroll
                 for (int a = 0; a < NI; ++a)
 #pragma unroll
-                    for (int b = 0; b < NJ; ++b) wr[(a * NJ + b) * JK_RED_STRIDE] = accJ[a][b];
+                    for (int b = 0; b < NJ; ++b) accJ[a][b] += __shfl_xor_sync(0xffffffffu, accJ[a][b], 16);
+                __syncwarp();
+                if (lane < 16) {
+#pragma unroll
+                    for (int a = 0; a < NI; ++a)
+#pragma unroll
+                        for (int b = 0; b < NJ; ++b) red_wr[(a * NJ + b) * JK_RED_STRIDE] = accJ[a][b];
+                }
                 __syncwarp();
                 const int v = lane >> 2;
-                const double *rd = s_red + v * JK_RED_STRIDE + (lane & 3) * 9;
+                const double *rd = s_red + v * JK_RED_STRIDE + (lane & 3) * 4;
                 double sum = 0.0;
                 if (v < R) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) sum += rd[e];
+                    for (int e = 0; e < 4; ++e) sum += rd[e];
                 }
                 sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 2);
