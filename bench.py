@@ -60,6 +60,15 @@ def parse():
     return ap.parse_args()
 
 
+def profiled_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/r01_traffic.json), per launch; None when no capture exists for this size."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(f"jk_pipe_rhf_n{n}", {}).get("dram_bytes")
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -272,7 +281,7 @@ def main():
             "eri_gbs_aggregate": nquad(n) * 8 / (ms_per_step * 1e-3) / 1e9,
             "frac_of_8tbs_per_gpu": nquad(n) * 8 / (ms_per_step * 1e-3) / 1e9 / world / 8000.0,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "jk_pipe_kernel", "kernel_ms": float(kt.item()),
+                         "traffic": profiled_traffic(n) if world == 1 else None, "kernel": "jk_pipe_kernel", "kernel_ms": float(kt.item()),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": float(ab.item())},
             "e2e": {"value": e2e_builds, "unit": "builds/s", "h2d_bytes_per_step": int(d_host.nbytes),
                     "d2h_bytes_per_step": int(2 * n * n * 8)},

@@ -20,7 +20,7 @@
  * Packed ERI layouts (8-fold symmetry, i>=j, k>=l, ij>=kl, ij = i(i+1)/2+j):
  *   canonical : offset ij(ij+1)/2 + kl, plain (ij|kl).
  *   native v1 : same row order; inside row ij the sub-row of k (l = 0..k, or 0..j when k == i) is
- *               padded to an even length (16-byte aligned sub-rows, zero pad cells); the stored value
+ *               padded to a multiple of 16 doubles (128-byte aligned sub-rows, zero pad cells); the stored value
  *               is (ij|kl) * 0.5^[i==j] * 0.5^[k==l] * 0.5^[ij==kl].  A rank holds the contiguous
  *               row range [ij_begin, ij_end) ("pair-block shard").
  */
@@ -55,8 +55,7 @@ int sqcc_ctx_synchronize(sqcc_ctx *ctx);
 /* ---- layout helpers (pure host arithmetic, usable without a GPU) --------------------------- */
 int64_t sqcc_npair(int n);
 int64_t sqcc_nquad(int n);
-/* Equal-area cut of the row range into `world` contiguous pair-block shards; cuts fall
- * on rows (i,0) with i a multiple of 4 so kernels can tile rows by i-block. */
+/* Equal-area cut of the row range into `world` contiguous pair-block shards, row granularity. */
 int sqcc_shard_rows(int n, int world, int rank, int64_t *ij_begin, int64_t *ij_end);
 /* Length in doubles of the native-v1 shard holding rows [ij_begin, ij_end). */
 int64_t sqcc_native_len(int n, int64_t ij_begin, int64_t ij_end);
@@ -85,8 +84,8 @@ int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full);
 int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_J, double *d_K);
 /* Same through host buffers (H2D of D, D2H of J/K inside; stream-synchronous). */
 int sqcc_jk_build_host(sqcc_ctx *ctx, const double *h_D, int nspin, int want_k, double *h_J, double *h_K);
-/* Select the kernel: 0 = TMA-pipelined tiled kernel (default), 1 = simple atomics kernel (cross-check),
- * 2 = tiled kernel with direct 128-bit global loads (no TMA staging). */
+/* Select the kernel: 0 = cp.async-pipelined warp-task kernel (default), 1 = simple atomics kernel (cross-check),
+ * 2 = warp-task kernel with direct 128-bit global loads, 16+c = pipelined kernel with tuning configuration c. */
 int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant);
 
 /* ---- LDA exchange grid quadrature: replaces hf_ksdft.py:426-440, :634-646 (rho), ksdft_functional.py
