@@ -268,7 +268,7 @@ int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full)
 
 int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant)
 {
-    SQCC_REQUIRE(ctx && variant >= 0 && (variant <= 2 || (variant >= 16 && variant <= 19)),
+    SQCC_REQUIRE(ctx && variant >= 0 && (variant <= 2 || (variant >= 16 && variant <= 23)),
                  "variant must be 0 (pipelined), 1 (simple), 2 (direct-load) or 16+cfg (pipelined, tuning cfg)");
     ctx->jk_variant = variant < 16 ? variant : 0;
     ctx->jk_cfg = variant >= 16 ? variant - 16 : 0;

@@ -106,7 +106,7 @@ struct sqcc_ctx {
     int64_t *d_rowoff = nullptr;  // [npair_local + 1] offsets relative to shard start
     int64_t *d_ioff = nullptr;    // [n + 1] offsets of rows (i,0) in the full native tensor
     int64_t shard_base = 0;       // offset of the shard's first row in the full native tensor
-    sqcc::JKSchedule sched[2];    // [0]: NI=4,NJ=2 (nspin 1);  [1]: NI=2,NJ=2 (nspin 2)
+    sqcc::JKSchedule sched[3];    // row-block shapes [0]: 4x2 (RHF, J-only)  [1]: 2x2 (UHF)  [2]: 4x4 (tuning)
     int jk_variant = 0;
     int jk_cfg = 0;  // tuning knob of the pipelined kernel (warps, stages), see launch_pipe
 

@@ -460,6 +460,7 @@ int jk_build_schedule(sqcc_ctx *ctx)
 {
     SQCC_TRY(build_one_schedule(ctx, ctx->sched[0], JK_NI, JK_NJ));
     SQCC_TRY(build_one_schedule(ctx, ctx->sched[1], 2, 2));
+    SQCC_TRY(build_one_schedule(ctx, ctx->sched[2], 4, 4));
     const size_t nl = (size_t)ctx->n * ctx->ldd;
     if (ctx->d_dwork) cudaFree(ctx->d_dwork);
     if (ctx->d_acc) cudaFree(ctx->d_acc);
@@ -548,7 +549,9 @@ int jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_
     ctx->launches++;
     SQCC_CUDA(cudaGetLastError());
 
-    const JKSchedule &sc = ctx->sched[(nspin == 2 && want_k) ? 1 : 0];
+    // default: 4x4 row-blocks (RHF, J-only), 2x2 for the dual-density UHF pass; cfg 1..3 select 4x2 tuning variants
+    const bool wide = ctx->jk_variant == 0 && (ctx->jk_cfg == 0 || ctx->jk_cfg == 4) && !(nspin == 2 && want_k);
+    const JKSchedule &sc = ctx->sched[(nspin == 2 && want_k) ? 1 : (wide ? 2 : 0)];
     JKParams p;
     p.P = ctx->d_eri;
     p.rowoff = ctx->d_rowoff;
@@ -580,6 +583,11 @@ int jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_
             jk_simple_kernel<2, true><<<grid, 256, 0, ctx->stream>>>(p, nrows, ctx->i_begin);
         ctx->launches++;
         SQCC_CUDA(cudaGetLastError());
+    } else if (wide && p.ntasks > 0) {
+        if (!want_k)
+            SQCC_TRY((launch_pipe_cfg<4, 4, 1, false, 8, 2, true, true>(ctx, p)));
+        else
+            SQCC_TRY((launch_pipe_cfg<4, 4, 1, true, 8, 2, true, true>(ctx, p)));
     } else if (ctx->jk_variant == 0 && p.ntasks > 0) {
         if (!want_k)
             SQCC_TRY((launch_pipe<JK_NI, JK_NJ, 1, false>(ctx, p)));

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
     constexpr int NS = WANTK ? NSPIN : 1;
     constexpr int NV = NS * (NI + NJ);  // lane-partial values reduced per sub-row
     static_assert(NV <= 8, "reduction scratch holds 8 values");
-    static_assert(NI * NJ <= 8, "reduction scratch holds 8 values");
+    static_assert(NI * NJ <= 16, "s_w holds 16 values");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wbase = smem_raw + (size_t)warp * WARP_BYTES;
@@ -405,26 +405,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                 for (int a = 0; a < NI; ++a)
 #pragma unroll
                     for (int b = 0; b < NJ; ++b) accJ[a][b] += __shfl_xor_sync(0xffffffffu, accJ[a][b], 16);
-                __syncwarp();
-                if (lane < 16) {
 #pragma unroll
-                    for (int a = 0; a < NI; ++a)
+                for (int h = 0; h < (R + 7) / 8; ++h) {   // eight row dots per pass through the scratch
+                    __syncwarp();
+                    if (lane < 16) {
 #pragma unroll
-                        for (int b = 0; b < NJ; ++b) red_wr[(a * NJ + b) * JK_RED_STRIDE] = accJ[a][b];
+                        for (int q = 0; q < 8; ++q)
+                            if (8 * h + q < R) red_wr[q * JK_RED_STRIDE] = accJ[(8 * h + q) / NJ][(8 * h + q) % NJ];
+                    }
+                    __syncwarp();
+                    const int v = 8 * h + (lane >> 2);
+                    const double *rd = s_red + (lane >> 2) * JK_RED_STRIDE + (lane & 3) * 4;
+                    double sum = 0.0;
+                    if (v < R) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) sum += rd[e];
+                    }
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    const int i = i0 + v / NJ, j = j0 + v % NJ;
+                    const bool ok = (lane & 3) == 0 && v < R && i < n && j <= i;  // rows outside the shard add 0
+                    red_add_if(ok, p.jt + (ok ? (size_t)i * ldd + j : 0), sum);
                 }
-                __syncwarp();
-                const int v = lane >> 2;
-                const double *rd = s_red + v * JK_RED_STRIDE + (lane & 3) * 4;
-                double sum = 0.0;
-                if (v < R) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) sum += rd[e];
-                }
-                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                const int i = i0 + v / NJ, j = j0 + v % NJ;
-                const bool ok = (lane & 3) == 0 && v < R && i < n && j <= i;  // rows outside the shard add 0
-                red_add_if(ok, p.jt + (ok ? (size_t)i * ldd + j : 0), sum);
             }
         }
         flushA();
