@@ -503,7 +503,8 @@ static int launch_pipe(sqcc_ctx *ctx, const JKParams &p)
 template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES, bool SLAB, bool RING>
 static int launch_pipe_cfg(sqcc_ctx *ctx, const JKParams &p)
 {
-    const size_t smem = (size_t)WARPS * jk_pipe_warp_bytes<NI, NJ, STAGES, SLAB, RING>();
+    constexpr int NVP = ((WANTK ? NSPIN : 1) * (NI + NJ) + 7) / 8;
+    const size_t smem = (size_t)WARPS * jk_pipe_warp_bytes<NI, NJ, STAGES, SLAB, RING, NVP>();
     auto kern = jk_pipe_kernel<NI, NJ, NSPIN, WANTK, WARPS, STAGES, SLAB, RING>;
     SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -551,7 +552,9 @@ int jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_
 
     // default: 4x4 row-blocks (RHF, J-only), 2x2 for the dual-density UHF pass; cfg 1..3 select 4x2 tuning variants
     const bool wide = ctx->jk_variant == 0 && (ctx->jk_cfg == 0 || ctx->jk_cfg == 4) && !(nspin == 2 && want_k);
-    const JKSchedule &sc = ctx->sched[(nspin == 2 && want_k) ? 1 : (wide ? 2 : 0)];
+    const bool uhf = nspin == 2 && want_k;
+    const bool uhf_wide = uhf && ctx->jk_variant == 0 && ctx->jk_cfg != 5;   // 4x2 row-blocks, two reduction passes
+    const JKSchedule &sc = ctx->sched[uhf ? (uhf_wide ? 0 : 1) : (wide ? 2 : 0)];
     JKParams p;
     p.P = ctx->d_eri;
     p.rowoff = ctx->d_rowoff;
@@ -583,6 +586,8 @@ int jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_
             jk_simple_kernel<2, true><<<grid, 256, 0, ctx->stream>>>(p, nrows, ctx->i_begin);
         ctx->launches++;
         SQCC_CUDA(cudaGetLastError());
+    } else if (uhf_wide && p.ntasks > 0) {
+        SQCC_TRY((launch_pipe_cfg<4, 2, 2, true, 8, 2, true, true>(ctx, p)));
     } else if (wide && p.ntasks > 0) {
         if (!want_k)
             SQCC_TRY((launch_pipe_cfg<4, 4, 1, false, 8, 2, true, true>(ctx, p)));

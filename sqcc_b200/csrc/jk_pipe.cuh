@@ -46,12 +46,13 @@ __device__ __forceinline__ void red_add_if(bool pred, double *ptr, double v)
 
 constexpr int JK_RED_STRIDE = 17;  // value stride of the reduction scratch (odd: conflict-free 4x4 read pattern)
 
-template <int NI, int NJ, int STAGES, bool SLAB, bool RING>
+// NVP = number of 8-value passes of the per-sub-row reduction: ceil(nspin_k * (NI + NJ) / 8)
+template <int NI, int NJ, int STAGES, bool SLAB, bool RING, int NVP>
 constexpr int jk_pipe_warp_bytes()
 {
-    // J~ slab + (ring[STAGES][NI*NJ+1][512 B] | D2 tile slab) + uniform-operand staging [KN][8] + reduction scratch
-    return (SLAB ? JK_KN * 32 * 16 : 0) + (RING ? STAGES * (NI * NJ + 1) * 512 : JK_KN * 32 * 16) + JK_KN * 8 * 8 +
-           8 * JK_RED_STRIDE * 8 + 128;
+    // J~ slab + (ring[STAGES][NI*NJ+1][512 B] | D2 tile slab) + uniform-operand staging [KN][8 NVP] + reduction scratch
+    return (SLAB ? JK_KN * 32 * 16 : 0) + (RING ? STAGES * (NI * NJ + 1) * 512 : JK_KN * 32 * 16) +
+           JK_KN * 8 * NVP * 8 + 8 * NVP * JK_RED_STRIDE * 8 + 128;
 }
 
 // SLAB = true : J~[k, l-chunk] is accumulated over all row-blocks of a task in a warp-private shared-memory slab;
@@ -64,10 +65,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
 {
     constexpr int R = NI * NJ;
     constexpr int RS = R + 1;  // ring rows per stage: R ERI rows + the D2 tile row
-    constexpr int WARP_BYTES = jk_pipe_warp_bytes<NI, NJ, STAGES, SLAB, RING>();
     constexpr int NS = WANTK ? NSPIN : 1;
     constexpr int NV = NS * (NI + NJ);  // lane-partial values reduced per sub-row
-    static_assert(NV <= 8, "reduction scratch holds 8 values");
+    constexpr int NVP = (NV + 7) / 8;   // reduction passes (8 values per pass)
+    constexpr int WARP_BYTES = jk_pipe_warp_bytes<NI, NJ, STAGES, SLAB, RING, NVP>();
+    static_assert(NVP <= 2, "reduction scratch holds 16 values");
     static_assert(NI * NJ <= 16, "s_w holds 16 values");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -76,8 +78,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
     double2 *ring = s_jt + (SLAB ? JK_KN * 32 : 0);                               // [STAGES][RS][32]
     double2 *s_d2 = ring;                                            // [KN][32] (RING == false only)
     double *s_u = reinterpret_cast<double *>(ring + (RING ? STAGES * RS * 32 : JK_KN * 32));  // [KN][8]
-    double *s_red = s_u + JK_KN * 8;                                 // [8][JK_RED_STRIDE]
-    double *s_w = s_red + 8 * JK_RED_STRIDE;                         // [8] D2[i_a, j_b] of the row-block
+    double *s_red = s_u + JK_KN * 8 * NVP;                           // [8 NVP][JK_RED_STRIDE]
+    double *s_w = s_red + 8 * NVP * JK_RED_STRIDE;                         // [8] D2[i_a, j_b] of the row-block
     const uint32_t ring_u32 = smem_u32(ring) + 16u * lane;
     const int n = p.n, ldd = p.ldd;
     const size_t nl = (size_t)n * ldd;
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                     const int s = q / (NI + NJ), w = q % (NI + NJ);
                     int row = w < NI ? i0 + w : j0 + (w - NI);
                     row = row < n ? row : n - 1;
-                    s_u[lane * 8 + q] = __ldg(p.dsp + s * nl + (size_t)row * ldd + k);
+                    s_u[lane * (8 * NVP) + q] = __ldg(p.dsp + s * nl + (size_t)row * ldd + k);
                 }
             }
             __syncwarp();
@@ -280,22 +282,36 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
             // Reduction scheme: one xor-16 shuffle halves the partials to 16 lanes, which store them (1 wavefront per
             // value); lane t then sums 4 entries of value t>>2 (stride 17: the 4x4 read pattern of a half-warp is
             // conflict free) and two more shuffles finish the sum.
-            const int red_v = lane >> 2;   // value this lane sums (4 lanes per value, 4 scratch entries each)
-            const double *red_rd = s_red + red_v * JK_RED_STRIDE + (lane & 3) * 4;
+            // (pass h handles values 8h .. 8h+7: value 8h + (lane >> 2), 4 lanes per value, 4 scratch entries each)
+            const double *red_rd = s_red + (lane >> 2) * JK_RED_STRIDE + (lane & 3) * 4;
             double *red_wr = s_red + (lane & 15);
-            double *red_dst = p.kt;
-            bool red_ok = false;
-            if (WANTK) {
-                const int s = red_v / (NI + NJ), w = red_v % (NI + NJ);
-                const int row = w < NI ? i0 + w : j0 + (w - NI);
-                red_ok = (lane & 3) == 0 && red_v < NV && row < n;
-                if (red_ok) red_dst = p.kt + s * nl + (size_t)row * ldd;
+            double *red_dst[NVP];
+            bool red_ok[NVP];
+#pragma unroll
+            for (int h = 0; h < NVP; ++h) {
+                red_dst[h] = p.kt;
+                red_ok[h] = false;
+                if (WANTK) {
+                    const int v = 8 * h + (lane >> 2);
+                    const int s = v / (NI + NJ), w = v % (NI + NJ);
+                    const int row = w < NI ? i0 + w : j0 + (w - NI);
+                    red_ok[h] = (lane & 3) == 0 && v < NV && row < n;
+                    if (red_ok[h]) red_dst[h] = p.kt + s * nl + (size_t)row * ldd;
+                }
             }
-            auto red_finish = [&](const double (&r4)[4], int k) {
-                double sum = (r4[0] + r4[1]) + (r4[2] + r4[3]);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                red_add_if(red_ok, red_dst + (red_ok ? k : 0), sum);
+            auto red_finish = [&](int k) {
+#pragma unroll
+                for (int h = 0; h < NVP; ++h) {
+                    const double *rd = red_rd + 8 * h * JK_RED_STRIDE;
+                    const bool on = 8 * h + (lane >> 2) < NV;
+                    double r4[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) r4[e] = on ? rd[e] : 0.0;
+                    double sum = (r4[0] + r4[1]) + (r4[2] + r4[3]);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    red_add_if(red_ok[h], red_dst[h] + (red_ok[h] ? k : 0), sum);
+                }
             };
 
             for (int kk = kk_lo; kk < kk_hi; ++kk) {
@@ -313,9 +329,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                     if (prod_it < niter) issue_next();   // next sub-row's loads fly during this FMA block
                 }
 
-                double u[8];
+                double u[8 * NVP];
                 if (WANTK) {
-                    const double2 *up = reinterpret_cast<const double2 *>(s_u + kk * 8);
+                    const double2 *up = reinterpret_cast<const double2 *>(s_u + kk * 8 * NVP);
 #pragma unroll
                     for (int q = 0; q < (NV + 1) / 2; ++q) {
                         const double2 w = up[q];
@@ -325,9 +341,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                 }
                 const double2 d2 = RING ? buf[R * 32] : s_d2[kk * 32 + lane];
                 double2 jt2 = make_double2(0.0, 0.0);
-                double cd[8];
+                double cd[8 * NVP];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) cd[q] = 0.0;
+                for (int q = 0; q < 8 * NVP; ++q) cd[q] = 0.0;
 #pragma unroll
                 for (int a = 0; a < NI; ++a)
 #pragma unroll
@@ -364,12 +380,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                     red_add_if(ok && l0 + 1 <= k, dst + 1, jt2.y);
                 }
                 if (WANTK) {
-                    if (kk > kk_lo) {   // previous sub-row's partials: written one iteration ago, so no store->load stall
-                        double r4[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) r4[e] = (red_v < NV) ? red_rd[e] : 0.0;
-                        red_finish(r4, k - 1);
-                    }
+                    if (kk > kk_lo) red_finish(k - 1);   // previous sub-row's partials, written one iteration ago
                     // publish this sub-row's NV lane partials (conflict-free shared-memory transpose)
 #pragma unroll
                     for (int q = 0; q < NV; ++q) cd[q] += __shfl_xor_sync(0xffffffffu, cd[q], 16);
@@ -382,10 +393,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                 }
             }
             if (WANTK) {   // last sub-row of the sweep
-                double r4[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) r4[e] = (red_v < NV) ? red_rd[e] : 0.0;
-                red_finish(r4, k0 + kk_hi - 1);
+                red_finish(k0 + kk_hi - 1);
             }
 
             if (WANTK) {
