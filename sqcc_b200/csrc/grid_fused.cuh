@@ -1,0 +1,246 @@
+// Fused LDA grid kernels for N <= 64 AOs (N even): persistent CTAs, cp.async double-buffered phi tiles, FP64 DMMA.
+//
+//   grid_rho_lda_kernel : rho_n = phi_n D phi_n^T per spin, v_x / E_x point functions fused in the epilogue
+//                         (hf_ksdft.py:426-440, :634-646; ksdft_functional.py:41-177).  The (128 x N)(N x N) product
+//                         of a tile stays in registers and is dotted with the SAME shared-memory phi tile.
+//   grid_vxc_kernel     : V_pq = sum_n phi_np (w_n v_n) phi_nq (hf_ksdft.py:456-476).  A (= phi^T scaled) and B (= phi)
+//                         fragments come from one shared tile; each CTA keeps its 64 x 64 partial in registers over
+//                         its whole grid-point range and flushes it once with red.global.add.f64.
+// Shared tiles are [rows][68] doubles: stride 68 == 4 (mod 16) makes every m8n8k4 fragment load conflict free.
+// Larger / odd N use the generic tiled GEMM path (gemm_f64.cuh).
+#pragma once
+#include "gemm_f64.cuh"
+
+namespace sqcc {
+
+constexpr int GF_TM = 128;      // grid points per tile
+constexpr int GF_LD = 68;       // shared row stride (doubles)
+constexpr int GF_WARPS = 8;
+
+__device__ __forceinline__ void gf_cp16(void *dst, const void *src, bool on)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(on ? 16u : 0u) : "memory");
+}
+
+// Copy tile `t` (rows t*128 .. +128 of phi[G][n], n even) into At[128][68]; rows past G are zero-filled.
+__device__ __forceinline__ void gf_load_tile(double *At, const double *__restrict__ phi, int64_t G, int n, int64_t t)
+{
+    const int half = n >> 1;
+    const int chunks = GF_TM * half;
+    const int64_t g0 = t * GF_TM;
+    for (int c = threadIdx.x; c < chunks; c += GF_WARPS * 32) {
+        const int r = c / half, cc = c - r * half;
+        const bool on = g0 + r < G;
+        gf_cp16(At + r * GF_LD + 2 * cc, phi + (on ? (g0 + r) * n + 2 * cc : 0), on);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int NSPIN>
+__global__ void __launch_bounds__(GF_WARPS * 32, 1)
+grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w, const double *__restrict__ D, int64_t G,
+                    int n, double c_pot, double c_en, double *__restrict__ rho_out, double *__restrict__ wv,
+                    double *__restrict__ exc)
+{
+    extern __shared__ __align__(128) double gsm[];
+    double *Ds = gsm;                               // [NSPIN][64][68]
+    double *At = Ds + NSPIN * 64 * GF_LD;           // [2][128][68]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // zero everything once (pad columns / rows must stay finite), then stage D
+    for (int e = tid; e < NSPIN * 64 * GF_LD + 2 * GF_TM * GF_LD; e += GF_WARPS * 32) gsm[e] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < NSPIN * n * n; e += GF_WARPS * 32) {
+        const int s = e / (n * n), r = (e / n) % n, c = e % n;
+        Ds[(s * 64 + r) * GF_LD + c] = D[e];
+    }
+    const int64_t ntiles = (G + GF_TM - 1) / GF_TM;
+    const int ksteps = (n + 3) >> 2;
+    double exc_part = 0.0;
+    int buf = 0;
+    if ((int64_t)blockIdx.x < ntiles) gf_load_tile(At, phi, G, n, blockIdx.x);
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t tn = t + gridDim.x;
+        __syncthreads();   // everyone is done with the buffer that is refilled next (and D is staged)
+        if (tn < ntiles) {
+            gf_load_tile(At + (buf ^ 1) * GF_TM * GF_LD, phi, G, n, tn);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double *A = At + buf * GF_TM * GF_LD + (warp * 16) * GF_LD;   // this warp's 16 rows
+#pragma unroll
+        for (int s = 0; s < NSPIN; ++s) {
+            double acc[2][8][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            const double *B = Ds + s * 64 * GF_LD;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int kq = 4 * ks + (lane & 3);
+                const double a0 = A[(lane >> 2) * GF_LD + kq], a1 = A[(8 + (lane >> 2)) * GF_LD + kq];
+                double b[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = B[kq * GF_LD + 8 * j + (lane >> 2)];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, b[j]);
+                    dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, b[j]);
+                }
+            }
+            // rho = rowdot(T, phi): lane holds T[row = lane/4 (+8)][col = 8j + 2(lane%4) + {0,1}]
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = 8 * i + (lane >> 2);
+                double part = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const double2 x = *reinterpret_cast<const double2 *>(A + row * GF_LD + 8 * j + 2 * (lane & 3));
+                    part = fma(acc[i][j][0], x.x, fma(acc[i][j][1], x.y, part));
+                }
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                const int64_t g = t * GF_TM + warp * 16 + row;
+                if ((lane & 3) == 0 && g < G) {
+                    const double wg = w[g];
+                    if (rho_out) rho_out[s * G + g] = part;
+                    wv[s * G + g] = wg * (c_pot * pow(part, 1.0 / 3.0));   // pow like NumPy: NaN for rho < 0
+                    exc_part += wg * pow(part, 4.0 / 3.0);
+                }
+            }
+        }
+        buf ^= 1;
+    }
+    // E_x: block reduction, one atomic per CTA
+    __shared__ double red[GF_WARPS];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) exc_part += __shfl_xor_sync(0xffffffffu, exc_part, o);
+    if (lane == 0) red[warp] = exc_part;
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0;
+        for (int i = 0; i < GF_WARPS; ++i) sum += red[i];
+        atomicAdd(exc, c_en * sum);
+    }
+}
+
+template <int NSPIN>
+__global__ void __launch_bounds__(GF_WARPS * 32, 1)
+grid_vxc_kernel(const double *__restrict__ phi, const double *__restrict__ wv, int64_t G, int n, double *__restrict__ V)
+{
+    extern __shared__ __align__(128) double gsm[];
+    double *At = gsm;                               // [2][128][68]
+    double *Ws = At + 2 * GF_TM * GF_LD;            // [2][NSPIN][128]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < 2 * GF_TM * GF_LD + 2 * NSPIN * GF_TM; e += GF_WARPS * 32) gsm[e] = 0.0;
+    const int64_t ntiles = (G + GF_TM - 1) / GF_TM;
+    const int pt0 = 2 * (warp >> 1), qt0 = 4 * (warp & 1);   // this warp's 2 p-tiles x 4 q-tiles of the 64 x 64 output
+    double acc[NSPIN][2][4][2];
+#pragma unroll
+    for (int s = 0; s < NSPIN; ++s)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[s][i][j][0] = acc[s][i][j][1] = 0.0;
+    auto load_w = [&](int b, int64_t t) {
+        for (int e = tid; e < NSPIN * GF_TM; e += GF_WARPS * 32) {
+            const int s = e / GF_TM, r = e % GF_TM;
+            const int64_t g = t * GF_TM + r;
+            Ws[(b * NSPIN + s) * GF_TM + r] = g < G ? wv[s * G + g] : 0.0;
+        }
+    };
+    int buf = 0;
+    __syncthreads();
+    if ((int64_t)blockIdx.x < ntiles) {
+        gf_load_tile(At, phi, G, n, blockIdx.x);
+        load_w(0, blockIdx.x);
+    }
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t tn = t + gridDim.x;
+        __syncthreads();
+        if (tn < ntiles) {
+            gf_load_tile(At + (buf ^ 1) * GF_TM * GF_LD, phi, G, n, tn);
+            load_w(buf ^ 1, tn);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double *A = At + buf * GF_TM * GF_LD;
+        const double *Wt = Ws + buf * NSPIN * GF_TM;
+#pragma unroll 2
+        for (int ks = 0; ks < GF_TM / 4; ++ks) {
+            const int gq = 4 * ks + (lane & 3);           // grid point (k index) of this lane's fragment element
+            const double *row = A + gq * GF_LD + (lane >> 2);
+            double fa[2], fb[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) fa[i] = row[8 * (pt0 + i)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fb[j] = row[8 * (qt0 + j)];
+#pragma unroll
+            for (int s = 0; s < NSPIN; ++s) {
+                const double sc = Wt[s * GF_TM + gq];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double a = fa[i] * sc;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[s][i][j][0], acc[s][i][j][1], a, fb[j]);
+                }
+            }
+        }
+        buf ^= 1;
+    }
+    // flush the CTA's partial: lane holds V[p = 8 pt + lane/4][q = 8 qt + 2(lane%4) + {0,1}]
+#pragma unroll
+    for (int s = 0; s < NSPIN; ++s)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int pr = 8 * (pt0 + i) + (lane >> 2), q = 8 * (qt0 + j) + 2 * (lane & 3);
+                if (pr < n) {
+                    double *dst = V + (size_t)s * n * n + (size_t)pr * n + q;
+                    if (q < n) atomicAdd(dst, acc[s][i][j][0]);
+                    if (q + 1 < n) atomicAdd(dst + 1, acc[s][i][j][1]);
+                }
+            }
+}
+
+inline bool grid_fused_ok(const sqcc_ctx *ctx)
+{
+    return ctx->grid_n <= 64 && (ctx->grid_n & 1) == 0 && (reinterpret_cast<uintptr_t>(ctx->d_phi) & 15) == 0;
+}
+
+template <int NSPIN>
+static int launch_rho_lda(sqcc_ctx *ctx, const double *d_D, double c_pot, double c_en, double *d_rho, double *d_wv,
+                          double *d_exc)
+{
+    const size_t smem = sizeof(double) * (NSPIN * 64 * GF_LD + 2 * GF_TM * GF_LD);
+    auto kern = grid_rho_lda_kernel<NSPIN>;
+    SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (ctx->G + GF_TM - 1) / GF_TM;
+    const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
+    kern<<<grid, GF_WARPS * 32, smem, ctx->stream>>>(ctx->d_phi, ctx->d_w, d_D, ctx->G, ctx->grid_n, c_pot, c_en, d_rho,
+                                                     d_wv, d_exc);
+    ctx->launches++;
+    SQCC_CUDA(cudaGetLastError());
+    return SQCC_OK;
+}
+
+template <int NSPIN>
+static int launch_vxc(sqcc_ctx *ctx, const double *d_wv, double *d_V)
+{
+    const size_t smem = sizeof(double) * (2 * GF_TM * GF_LD + 2 * NSPIN * GF_TM);
+    auto kern = grid_vxc_kernel<NSPIN>;
+    SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (ctx->G + GF_TM - 1) / GF_TM;
+    const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
+    kern<<<grid, GF_WARPS * 32, smem, ctx->stream>>>(ctx->d_phi, d_wv, ctx->G, ctx->grid_n, d_V);
+    ctx->launches++;
+    SQCC_CUDA(cudaGetLastError());
+    return SQCC_OK;
+}
+
+}  // namespace sqcc

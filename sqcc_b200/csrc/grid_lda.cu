@@ -9,7 +9,7 @@
 // never written); V_xc is a split-K GEMM (N x G)(G x N) with the w*v scaling fused into the A-operand load.
 #include <math.h>
 
-#include "gemm_f64.cuh"
+#include "grid_fused.cuh"
 
 namespace sqcc {
 
@@ -130,6 +130,10 @@ int grid_quadrature(sqcc_ctx *ctx, const double *d_v, double *d_V)
     mul_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_w, d_v, ctx->G, wv);
     ctx->launches++;
     SQCC_CUDA(cudaGetLastError());
+    if (grid_fused_ok(ctx)) {
+        SQCC_CUDA(cudaMemsetAsync(d_V, 0, sizeof(double) * ctx->grid_n * ctx->grid_n, ctx->stream));
+        return launch_vxc<1>(ctx, wv, d_V);
+    }
     return vxc_gemm(ctx, wv, 1, d_V);
 }
 
@@ -140,8 +144,6 @@ int lda_vxc(sqcc_ctx *ctx, const double *d_D, int nspin, double *d_Vxc, double *
     SQCC_TRY(ensure_gridwork(ctx, sizeof(double) * 4 * G));
     double *rho = d_rho ? d_rho : ctx->d_gridwork;  // [nspin][G]
     double *wv = ctx->d_gridwork + 2 * G;           // [nspin][G]
-    SQCC_TRY(timer_start(ctx, 2));
-    SQCC_TRY(rho_gemm(ctx, d_D, nspin, rho));
     // constants exactly as ksdft_functional.py:59, :89, :125, :173 evaluate them
     const double cx = pow(3.0 / M_PI, 1.0 / 3.0);
     double c_pot = -cx, c_en = (-3.0 / 4.0) * cx;
@@ -150,6 +152,21 @@ int lda_vxc(sqcc_ctx *ctx, const double *d_D, int nspin, double *d_Vxc, double *
         c_en = (-3.0 / 4.0) * cx * pow(2.0, 1.0 / 3.0);
     }
     SQCC_CUDA(cudaMemsetAsync(d_Exc, 0, sizeof(double), ctx->stream));
+    if (grid_fused_ok(ctx)) {   // N <= 64: persistent fused DMMA kernels (grid_fused.cuh)
+        const int n = ctx->grid_n;
+        SQCC_TRY(timer_start(ctx, 2));
+        if (nspin == 1) SQCC_TRY(launch_rho_lda<1>(ctx, d_D, c_pot, c_en, rho, wv, d_Exc));
+        else SQCC_TRY(launch_rho_lda<2>(ctx, d_D, c_pot, c_en, rho, wv, d_Exc));
+        SQCC_TRY(timer_stop(ctx, 2));
+        SQCC_TRY(timer_start(ctx, 3));
+        SQCC_CUDA(cudaMemsetAsync(d_Vxc, 0, sizeof(double) * nspin * n * n, ctx->stream));
+        if (nspin == 1) SQCC_TRY(launch_vxc<1>(ctx, wv, d_Vxc));
+        else SQCC_TRY(launch_vxc<2>(ctx, wv, d_Vxc));
+        SQCC_TRY(timer_stop(ctx, 3));
+        return SQCC_OK;
+    }
+    SQCC_TRY(timer_start(ctx, 2));
+    SQCC_TRY(rho_gemm(ctx, d_D, nspin, rho));
     lda_pointwise_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(rho, ctx->d_w, G, nspin, c_pot, c_en, wv, d_Exc);
     ctx->launches++;
     SQCC_CUDA(cudaGetLastError());
