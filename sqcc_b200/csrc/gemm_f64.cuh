@@ -1,12 +1,16 @@
-// FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) GEMM used by the grid quadrature and the AO->MO transforms.
+// FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) GEMM used by the grid quadrature (generic N) and the AO->MO transforms.
 //
 //   C[m,n] (+)= sum_k  A(m,k) * scale[k] * B(k,n)
 //
 // tcgen05 has no FP64 kind and wgmma does not exist on sm_100, so FP64 tensor work on B200 is the warp-level
-// DMMA family.  CTA tile 64x64x16, 4 warps, each warp a 32x32 sub-tile (4x4 m8n8 accumulators in registers),
-// operands staged through shared memory in k-major layout with a row stride of 68 doubles (== 4 mod 16):
-// the four k-rows of a fragment then land on disjoint banks, so fragment loads are conflict free.
+// DMMA family.  CTA tile BM x 64 x 16 (BM = 64 or 32), 4 warps as 2 x 2, each warp a (BM/2) x 32 sub-tile
+// (m8n8 accumulators in registers), operands staged through shared memory in k-major layout with a row stride
+// == 4 (mod 16): the four k-rows of a fragment land on disjoint banks, so fragment loads are conflict free.
 // Global -> shared staging is register double-buffered (next tile's loads are in flight during the MMAs).
+// B operand addressing modes (the MP2 transforms read symmetric-packed intermediates without expanding them):
+//   B_ROWS   : B(k,n) = B[k*sb_k + n]
+//   B_KOFF   : B(k,n) = B[koff[k] + n]                    (row offsets from a table, e.g. pair(p,q)*npair)
+//   B_SYMPK  : B(k,n) = B[pair(max(k,n), min(k,n))]       (symmetric matrix stored as a packed lower triangle)
 #pragma once
 #include "common.cuh"
 
@@ -17,6 +21,7 @@ enum GemmEpilogue {
     EPI_ATOMIC = 1,      // C += acc (split-K partial sums, red.global.add.f64)
     EPI_ROWDOT = 2       // out[m] += sum_n acc[m,n] * X[m,n]   (X has the shape/strides of C)
 };
+enum GemmBMode { B_ROWS = 0, B_KOFF = 1, B_SYMPK = 2 };
 
 struct GemmArgs {
     const double *A;
@@ -24,16 +29,17 @@ struct GemmArgs {
     double *C;            // EPI_ROWDOT: out vector [M] (per batch: + z * batch_c)
     const double *X;      // EPI_ROWDOT only
     const double *scale;  // optional per-k scale (nullptr = 1)
+    const int64_t *koff;  // B_KOFF only: [batch][K] row offsets
     int M, N, K;
     int64_t sa_m, sa_k;   // A(m,k) = A[m*sa_m + k*sa_k]
-    int64_t sb_k;         // B(k,n) = B[k*sb_k + n]
+    int64_t sb_k;         // B_ROWS: B(k,n) = B[k*sb_k + n]
     int64_t sc_m;         // C(m,n) = C[m*sc_m + n]   (and X)
     int batch;            // blockIdx.z = batch * splitk + split
-    int64_t batch_a, batch_b, batch_c, batch_scale;
+    int64_t batch_a, batch_b, batch_c, batch_scale, batch_koff;
     int splitk;           // K is cut into `splitk` contiguous ranges (EPI_ATOMIC / EPI_ROWDOT only)
 };
 
-constexpr int GEMM_BM = 64, GEMM_BN = 64, GEMM_BK = 16, GEMM_LDS = 68, GEMM_THREADS = 128;
+constexpr int GEMM_BN = 64, GEMM_BK = 16, GEMM_THREADS = 128;
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
 {
@@ -42,38 +48,41 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-template <bool A_MFAST, int EPI>
+template <bool A_MFAST, int EPI, int BMODE, int BM>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g)
 {
-    __shared__ double As[2][GEMM_BK][GEMM_LDS];
-    __shared__ double Bs[2][GEMM_BK][GEMM_LDS];
+    constexpr int LDA_S = BM + 4, LDB_S = GEMM_BN + 4;   // 68 / 36: == 4 (mod 16)
+    constexpr int MT = BM / 16;                          // m8 tiles per warp
+    constexpr int EA = BM * GEMM_BK / GEMM_THREADS;      // A elements staged per thread
+    __shared__ double As[2][GEMM_BK][LDA_S];
+    __shared__ double Bs[2][GEMM_BK][LDB_S];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
-    const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * GEMM_BN;
+    const int wm = (warp >> 1) * (BM / 2), wn = (warp & 1) * 32;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * GEMM_BN;
     const int z = blockIdx.z, bz = z / g.splitk, sz = z % g.splitk;
     const double *A = g.A + (int64_t)bz * g.batch_a;
     const double *B = g.B + (int64_t)bz * g.batch_b;
     const double *scale = g.scale ? g.scale + (int64_t)bz * g.batch_scale : nullptr;
+    const int64_t *koff = BMODE == B_KOFF ? g.koff + (int64_t)bz * g.batch_koff : nullptr;
     // split-K range (multiples of BK)
     const int ktiles = (g.K + GEMM_BK - 1) / GEMM_BK;
     const int per = (ktiles + g.splitk - 1) / g.splitk;
     const int kt_lo = sz * per, kt_hi = (kt_lo + per) < ktiles ? (kt_lo + per) : ktiles;
 
-    double acc[4][4][2];
+    double acc[MT][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // staging registers: 1024 elements per operand tile / 128 threads = 8 each
-    double ra[8], rb[8];
+    double ra[EA], rb[8];
     auto load_tile = [&](int kt) {
         const int kbase = kt * GEMM_BK;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < EA; ++e) {
             const int idx = tid + e * GEMM_THREADS;
             int m, k;
-            if (A_MFAST) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
+            if (A_MFAST) { m = idx % BM; k = idx / BM; } else { k = idx & 15; m = idx >> 4; }
             const int gm = m0 + m, gk = kbase + k;
             double v = 0.0;
             if (gm < g.M && gk < g.K) {
@@ -81,18 +90,35 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
                 if (scale) v *= __ldg(scale + gk);
             }
             ra[e] = v;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tid + e * GEMM_THREADS;
             const int n = idx & 63, kb = idx >> 6;
             const int gn = n0 + n, gkb = kbase + kb;
-            rb[e] = (gn < g.N && gkb < g.K) ? __ldg(B + (int64_t)gkb * g.sb_k + gn) : 0.0;
+            double v = 0.0;
+            if (gn < g.N && gkb < g.K) {
+                if (BMODE == B_ROWS) v = __ldg(B + (int64_t)gkb * g.sb_k + gn);
+                else if (BMODE == B_KOFF) v = __ldg(B + __ldg(koff + gkb) + gn);
+                else {
+                    const int64_t hi = gkb > gn ? gkb : gn, lo = gkb > gn ? gn : gkb;
+                    v = __ldg(B + hi * (hi + 1) / 2 + lo);
+                }
+            }
+            rb[e] = v;
         }
     };
     auto store_tile = [&](int buf) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < EA; ++e) {
             const int idx = tid + e * GEMM_THREADS;
             int m, k;
-            if (A_MFAST) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
+            if (A_MFAST) { m = idx % BM; k = idx / BM; } else { k = idx & 15; m = idx >> 4; }
             As[buf][k][m] = ra[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tid + e * GEMM_THREADS;
             Bs[buf][idx >> 6][idx & 63] = rb[e];
         }
     };
@@ -106,13 +132,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
             if (kt + 1 < kt_hi) load_tile(kt + 1);
 #pragma unroll
             for (int ks = 0; ks < GEMM_BK; ks += 4) {
-                double af[4], bf[4];
+                double af[MT], bf[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) af[i] = As[buf][ks + (lane & 3)][wm + i * 8 + (lane >> 2)];
+                for (int i = 0; i < MT; ++i) af[i] = As[buf][ks + (lane & 3)][wm + i * 8 + (lane >> 2)];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) bf[j] = Bs[buf][ks + (lane & 3)][wn + j * 8 + (lane >> 2)];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < MT; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
@@ -127,7 +153,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
     if (EPI == EPI_ROWDOT) {
         double *out = g.C + (int64_t)bz * g.batch_c;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < MT; ++i) {
             const int gm = m0 + wm + i * 8 + (lane >> 2);
             double part = 0.0;
 #pragma unroll
@@ -145,7 +171,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
     } else {
         double *C = g.C + (int64_t)bz * g.batch_c;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < MT; ++i) {
             const int gm = m0 + wm + i * 8 + (lane >> 2);
             if (gm >= g.M) continue;
 #pragma unroll
@@ -164,23 +190,36 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
     }
 }
 
-inline int gemm_f64(sqcc_ctx *ctx, const GemmArgs &g, int epi)
+// bmode / small-M tiles are only instantiated for the A-transposed STORE form the AO->MO transforms use.
+inline int gemm_f64(sqcc_ctx *ctx, const GemmArgs &g, int epi, int bmode = B_ROWS)
 {
     SQCC_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0 && g.batch > 0 && g.splitk > 0, "bad GEMM shape");
     SQCC_REQUIRE(g.sa_m == 1 || g.sa_k == 1, "GEMM A operand needs a unit stride");
     SQCC_REQUIRE(epi != EPI_STORE || g.splitk == 1, "split-K needs an accumulating epilogue");
-    dim3 grid((g.N + GEMM_BN - 1) / GEMM_BN, (g.M + GEMM_BM - 1) / GEMM_BM, g.batch * g.splitk);
-    SQCC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "GEMM grid too large");
     const bool mfast = g.sa_m == 1 && g.sa_k != 1;
-#define SQCC_GEMM_LAUNCH(MF, E) gemm_f64_kernel<MF, E><<<grid, GEMM_THREADS, 0, ctx->stream>>>(g)
-    if (mfast) {
-        if (epi == EPI_STORE) SQCC_GEMM_LAUNCH(true, EPI_STORE);
-        else if (epi == EPI_ATOMIC) SQCC_GEMM_LAUNCH(true, EPI_ATOMIC);
-        else SQCC_GEMM_LAUNCH(true, EPI_ROWDOT);
+    const bool small_m = g.M <= 32 && mfast && epi == EPI_STORE;
+    SQCC_REQUIRE(bmode == B_ROWS || (mfast && epi == EPI_STORE), "packed B operands need the A^T / STORE form");
+    const int bm = small_m ? 32 : 64;
+    dim3 grid((g.N + GEMM_BN - 1) / GEMM_BN, (g.M + bm - 1) / bm, g.batch * g.splitk);
+    SQCC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "GEMM grid too large");
+#define SQCC_GEMM_LAUNCH(MF, E, BMD, BMV) gemm_f64_kernel<MF, E, BMD, BMV><<<grid, GEMM_THREADS, 0, ctx->stream>>>(g)
+    if (mfast && epi == EPI_STORE) {
+        if (small_m) {
+            if (bmode == B_ROWS) SQCC_GEMM_LAUNCH(true, EPI_STORE, B_ROWS, 32);
+            else if (bmode == B_KOFF) SQCC_GEMM_LAUNCH(true, EPI_STORE, B_KOFF, 32);
+            else SQCC_GEMM_LAUNCH(true, EPI_STORE, B_SYMPK, 32);
+        } else {
+            if (bmode == B_ROWS) SQCC_GEMM_LAUNCH(true, EPI_STORE, B_ROWS, 64);
+            else if (bmode == B_KOFF) SQCC_GEMM_LAUNCH(true, EPI_STORE, B_KOFF, 64);
+            else SQCC_GEMM_LAUNCH(true, EPI_STORE, B_SYMPK, 64);
+        }
+    } else if (mfast) {
+        if (epi == EPI_ATOMIC) SQCC_GEMM_LAUNCH(true, EPI_ATOMIC, B_ROWS, 64);
+        else SQCC_GEMM_LAUNCH(true, EPI_ROWDOT, B_ROWS, 64);
     } else {
-        if (epi == EPI_STORE) SQCC_GEMM_LAUNCH(false, EPI_STORE);
-        else if (epi == EPI_ATOMIC) SQCC_GEMM_LAUNCH(false, EPI_ATOMIC);
-        else SQCC_GEMM_LAUNCH(false, EPI_ROWDOT);
+        if (epi == EPI_STORE) SQCC_GEMM_LAUNCH(false, EPI_STORE, B_ROWS, 64);
+        else if (epi == EPI_ATOMIC) SQCC_GEMM_LAUNCH(false, EPI_ATOMIC, B_ROWS, 64);
+        else SQCC_GEMM_LAUNCH(false, EPI_ROWDOT, B_ROWS, 64);
     }
 #undef SQCC_GEMM_LAUNCH
     ctx->launches++;

@@ -3,13 +3,17 @@
 //   (pq|rs) -> (iq|rs) -> (iq|js) -> (ia|js) -> (ia|jb)        mp2.py:123-170
 //   E_corr = sum_ijab (2 x^2 - x x') / (e_i + e_j - e_a - e_b),  x = (ia|jb), x' = (ib|ja)
 //                                                               mp2.py:89-99, :240-254
-// The reference repeats the identical transform a second time for (ib|ja) (mp2.py:185-228); the result is
-// the same array, so it is read transposed instead.  Each quarter is a (batched) DMMA GEMM (gemm_f64.cuh):
-//   Q1  [n1 x N^3]        = C1^T [n1 x N] . E [N x N^3]
-//   Q2  per (a,q): [n3 x N] = C3^T [n3 x N] . T1_aq [N x N]
-//   Q3  per a:  [n2 x n3 N] = C2^T [n2 x N] . T2_a [N x n3 N]
-//   Q4  [n1 n2 n3 x n4]   = T3 [n1 n2 n3 x N] . C4 [N x n4]
-// E is the full tensor expanded once from the packed resident copy (eri_unpack_full).
+// The reference repeats the identical transform a second time for (ib|ja) (mp2.py:185-228); the result is the same
+// array, so it is read transposed instead.  The full N^4 tensor is never materialised:
+//   S   [npair x npair]      the packed lower triangle of the pair matrix, symmetrised by a tiled transpose
+//   Q1  per q: [n1 x npair]  = C1^T [n1 x N] . S[pair(p,q), :]      (B rows addressed through an offset table;
+//                              only canonical pairs rs are transformed: half the flops of the reference's step 1)
+//   Q2  per (a,q): [n3 x N]  = C3^T [n3 x N] . T1_aq (symmetric in (r,s), read from its packed lower triangle)
+//   Q3  per a:  [n2 x n3 N]  = C2^T [n2 x N] . T2_a [N x n3 N]
+//   Q4  [n1 n2 n3 x n4]      = T3 [n1 n2 n3 x N] . C4 [N x n4]
+// Each quarter is a (batched) DMMA GEMM (gemm_f64.cuh).
+#include <math.h>
+
 #include "gemm_f64.cuh"
 
 namespace sqcc {
@@ -25,59 +29,120 @@ static int ensure_mp2work(sqcc_ctx *ctx, size_t bytes)
     return SQCC_OK;
 }
 
+__device__ __forceinline__ void pair_unrank_dev(int64_t ij, int &i, int &j)
+{
+    int64_t t = (int64_t)((sqrt(8.0 * (double)ij + 1.0) - 1.0) * 0.5);
+    while (t * (t + 1) / 2 > ij) --t;
+    while ((t + 1) * (t + 2) / 2 <= ij) ++t;
+    i = (int)t;
+    j = (int)(ij - t * (t + 1) / 2);
+}
+
+// S[pq][rs] = (pq|rs) for all pair indices: 32 x 32 tiles of the packed lower triangle are read along rows
+// (mostly contiguous in the native layout), written as they are and written transposed through shared memory.
+__global__ void __launch_bounds__(256) symmetrize_pairs_kernel(const double *__restrict__ P,
+                                                               const int64_t *__restrict__ rowoff, int64_t npair,
+                                                               int64_t ntile, double *__restrict__ S)
+{
+    __shared__ double tile[32][33];
+    // blockIdx.x enumerates tile pairs (tr >= tc)
+    const int64_t b = blockIdx.x;
+    int tr, tc;
+    pair_unrank_dev(b, tr, tc);
+    const int64_t R0 = (int64_t)tr * 32, C0 = (int64_t)tc * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t rs = C0 + lane;
+    int k = 0, l = 0;
+    if (rs < npair) pair_unrank_dev(rs, k, l);
+    const int64_t coloff = subrow_offset(k) + l;
+    for (int r = warp; r < 32; r += 8) {
+        const int64_t pq = R0 + r;
+        double v = 0.0;
+        if (pq < npair && rs <= pq) {
+            int i, j;
+            pair_unrank_dev(pq, i, j);
+            v = P[rowoff[pq] + coloff] / degeneracy(i, j, k, l);
+            S[pq * npair + rs] = v;
+        }
+        tile[r][lane] = v;
+    }
+    __syncthreads();
+    for (int r = warp; r < 32; r += 8) {
+        // element (pq = R0 + lane, rs = C0 + r) goes to S[rs][pq]
+        const int64_t pq = R0 + lane, rs2 = C0 + r;
+        if (pq < npair && rs2 < pq) S[rs2 * npair + pq] = tile[lane][r];
+    }
+    (void)ntile;
+}
+
+__global__ void koff_kernel(int n, int64_t npair, int64_t *__restrict__ koff)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int q = idx / n, p = idx % n;
+    const int hi = p > q ? p : q, lo = p > q ? q : p;
+    koff[idx] = ((int64_t)hi * (hi + 1) / 2 + lo) * npair;   // row pair(p,q) of S
+}
+
 int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2, const double *d_C3, int n3,
           const double *d_C4, int n4, double *d_out)
 {
-    // C blocks are [N, n_x] row-major with leading dimension ld_x passed through n (columns of the AO x MO matrix):
-    // callers pass pointers into the [N,N] coefficient matrix, so the leading dimension is N.
-    const int64_t n = ctx->n;
-    const int64_t n3_ = n * n * n;
-    const size_t full = (size_t)n * n3_;
-    const size_t t1 = (size_t)n1 * n3_, t2 = (size_t)n1 * n * n3 * n, t3 = (size_t)n1 * n2 * n3 * n;
-    // workspace: [E full][T1][T2] ; T3 reuses T1's space (T1 is dead after Q2)
-    size_t t13 = t1 > t3 ? t1 : t3;
-    SQCC_TRY(ensure_mp2work(ctx, sizeof(double) * (full + t13 + t2)));
-    double *E = ctx->d_mp2work, *T1 = E + full, *T2 = T1 + t13, *T3 = T1;
-    SQCC_TRY(eri_unpack_full(ctx, E));
+    // C blocks are column blocks of an [N,N] AO x MO matrix: element (p, a) at C[p*N + a].
+    SQCC_REQUIRE(ctx->d_eri && ctx->ij_begin == 0 && ctx->ij_end == pair_index(ctx->n, 0),
+                 "the AO->MO transform needs an unsharded ERI attached");
+    const int64_t n = ctx->n, npair = n * (n + 1) / 2;
+    const size_t s_sz = (size_t)npair * npair;
+    const size_t t1 = (size_t)n1 * n * npair, t2 = (size_t)n1 * n * n3 * n, t3 = (size_t)n1 * n2 * n3 * n;
+    const size_t t13 = t1 > t3 ? t1 : t3;   // T3 reuses T1's space (T1 is dead after Q2)
+    const size_t koff_sz = (size_t)n * n;   // int64 entries, stored in the double workspace
+    SQCC_TRY(ensure_mp2work(ctx, sizeof(double) * (s_sz + t13 + t2 + koff_sz)));
+    double *S = ctx->d_mp2work, *T1 = S + s_sz, *T2 = T1 + t13, *T3 = T1;
+    int64_t *koff = reinterpret_cast<int64_t *>(T2 + t2);
+
+    {   // symmetrised pair matrix + row-offset table
+        const int64_t ntile = (npair + 31) / 32;
+        const int64_t nblk = ntile * (ntile + 1) / 2;
+        SQCC_REQUIRE(nblk < ((int64_t)1 << 31), "pair matrix too large for one launch");
+        symmetrize_pairs_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, npair, ntile, S);
+        koff_kernel<<<(unsigned)((n * n + 255) / 256), 256, 0, ctx->stream>>>((int)n, npair, koff);
+        ctx->launches += 2;
+        SQCC_CUDA(cudaGetLastError());
+    }
 
     GemmArgs g{};
     g.scale = nullptr;
     g.X = nullptr;
+    g.koff = nullptr;
     g.splitk = 1;
     g.batch_scale = 0;
-    // Q1: T1[a, (q r s)] = sum_p C1[p, a] E[p, (q r s)]
-    g.A = d_C1; g.sa_m = 1; g.sa_k = n;
-    g.B = E; g.sb_k = n3_;
-    g.C = T1; g.sc_m = n3_;
-    g.M = n1; g.N = (int)0; g.K = (int)n;
-    g.batch = 1; g.batch_a = g.batch_b = g.batch_c = 0;
-    // N^3 can exceed what one launch's grid.x handles comfortably; chunk the column range
+    g.batch_koff = 0;
+    // Q1: T1[a, q, rs] = sum_p C1[p, a] S[pair(p,q), rs]        batch over q, canonical pairs rs only
     {
-        const int64_t chunk = (int64_t)1 << 24;
-        for (int64_t c0 = 0; c0 < n3_; c0 += chunk) {
-            GemmArgs h = g;
-            h.B = E + c0;
-            h.C = T1 + c0;
-            h.N = (int)((n3_ - c0) < chunk ? (n3_ - c0) : chunk);
-            SQCC_TRY(gemm_f64(ctx, h, EPI_STORE));
-        }
+        GemmArgs h = g;
+        h.A = d_C1; h.sa_m = 1; h.sa_k = n;
+        h.B = S; h.sb_k = 0; h.koff = koff; h.batch_koff = n;
+        h.C = T1; h.sc_m = n * npair;
+        h.M = n1; h.N = (int)npair; h.K = (int)n;
+        h.batch = (int)n; h.batch_a = 0; h.batch_b = 0; h.batch_c = npair;
+        SQCC_REQUIRE(npair < ((int64_t)1 << 31), "npair too large");
+        SQCC_TRY(gemm_f64(ctx, h, EPI_STORE, B_KOFF));
     }
-    // Q2: T2[a, q, c, s] = sum_r C3[r, c] T1[a, q, r, s]     batch over (a, q)
+    // Q2: T2[a, q, c, s] = sum_r C3[r, c] T1[a, q, pair(r,s)]   batch over (a, q); T1_aq read as packed symmetric
     {
         const int64_t nb = (int64_t)n1 * n;
         const int64_t bmax = 32768;
         for (int64_t b0 = 0; b0 < nb; b0 += bmax) {
             GemmArgs h = g;
             h.A = d_C3; h.sa_m = 1; h.sa_k = n;
-            h.B = T1 + b0 * n * n; h.sb_k = n;
+            h.B = T1 + b0 * npair; h.sb_k = 0;
             h.C = T2 + b0 * n3 * n; h.sc_m = n;
             h.M = n3; h.N = (int)n; h.K = (int)n;
             h.batch = (int)((nb - b0) < bmax ? (nb - b0) : bmax);
-            h.batch_a = 0; h.batch_b = n * n; h.batch_c = (int64_t)n3 * n;
-            SQCC_TRY(gemm_f64(ctx, h, EPI_STORE));
+            h.batch_a = 0; h.batch_b = npair; h.batch_c = (int64_t)n3 * n;
+            SQCC_TRY(gemm_f64(ctx, h, EPI_STORE, B_SYMPK));
         }
     }
-    // Q3: T3[a, b, c, s] = sum_q C2[q, b] T2[a, q, c, s]     batch over a
+    // Q3: T3[a, b, c, s] = sum_q C2[q, b] T2[a, q, c, s]         batch over a
     {
         GemmArgs h = g;
         h.A = d_C2; h.sa_m = 1; h.sa_k = n;
@@ -90,7 +155,7 @@ int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2,
     // Q4: out[(a b c), d] = sum_s T3[(a b c), s] C4[s, d]
     {
         const int64_t rows = (int64_t)n1 * n2 * n3;
-        const int64_t rmax = (int64_t)65535 * GEMM_BM;
+        const int64_t rmax = (int64_t)65535 * 64;
         for (int64_t r0 = 0; r0 < rows; r0 += rmax) {
             GemmArgs h = g;
             h.A = T3 + r0 * n; h.sa_m = n; h.sa_k = 1;
