@@ -251,7 +251,11 @@ def main():
     k_ms = float(np.mean(ktimes))
     kt = torch.tensor([k_ms], dtype=torch.float64, device=eng.device)
     ab = torch.tensor([float(algo_bytes)], dtype=torch.float64, device=eng.device)
+    rank_ms = [k_ms]
     if world > 1:
+        gathered = [torch.zeros_like(kt) for _ in range(world)]
+        dist.all_gather(gathered, kt)
+        rank_ms = [float(x.item()) for x in gathered]
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
     achieved = float(ab.item()) / (float(kt.item()) * 1e-3) / 1e9  # GB/s on the slowest rank's shard
 
@@ -285,7 +289,7 @@ def main():
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": float(ab.item())},
             "e2e": {"value": e2e_builds, "unit": "builds/s", "h2d_bytes_per_step": int(d_host.nbytes),
                     "d2h_bytes_per_step": int(2 * n * n * 8)},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "rank_kernel_ms": rank_ms,
         }
         if world == 1:
             line["cpu_baseline"] = cpu_port_baseline(n, d_host, args.cpu_seconds)
@@ -317,6 +321,49 @@ def extras(eng, torch):
                     ts.append(eng.timings()["jk_kernel"])
             t = float(np.mean(ts))
             res[f"n{n}_{tag}"] = {"kernel_ms": t, "gbs": ab / (t * 1e-3) / 1e9, "builds_per_s_kernel": 1e3 / t}
+    # FP64 tensor-pipe work: LDA grid quadrature at the O2 def2-TZVP size and the MP2 AO->MO transforms at benzene size,
+    # against cuBLAS DGEMM (torch.matmul float64 8192^3) measured in the same run
+    a = torch.randn(8192, 8192, dtype=torch.float64, device=eng.device)
+    best = 1e9
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, a)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a
+    peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    res["fp64_dgemm_tflops_measured"] = peak
+    rng = np.random.default_rng(1)
+    g, n = 354200, 62
+    phi = rng.standard_normal((g, n)) * np.exp(-rng.uniform(0, 8, size=(g, 1)))
+    eng.attach_grid(phi, rng.uniform(0, 1e-2, size=g))
+    d = density_uhf(n, 9, 7, 3)
+    ts = []
+    for it in range(5):
+        eng.lda_vxc(d)
+        tm = eng.timings()
+        if it >= 2:
+            ts.append((tm["rho"], tm["vxc"]))
+    rho_ms, vxc_ms = np.mean(ts, axis=0)
+    fl = 2.0 * g * n * n * 2
+    res["lda_uks_G354200_N62"] = {"rho_ms": float(rho_ms), "vxc_ms": float(vxc_ms),
+                                  "rho_tflops": fl / (rho_ms * 1e-3) / 1e12, "vxc_tflops": fl / (vxc_ms * 1e-3) / 1e12,
+                                  "vxc_frac_of_dgemm": fl / (vxc_ms * 1e-3) / 1e12 / peak}
+    n, no = 222, 21
+    eng.attach_eri_synth(n, SEED)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    eps = np.concatenate([np.sort(rng.uniform(-2, -0.4, no)), np.sort(rng.uniform(0.0, 3.0, n - no))])
+    ts = []
+    for it in range(3):
+        eng.mp2_corr(q, eps, no)
+        if it >= 1:
+            ts.append(eng.timings()["mp2_transform"])
+    t = float(np.mean(ts))
+    nv = n - no
+    fl = 2.0 * no * n ** 4 + 2.0 * no * no * n ** 3 + 2.0 * no * no * nv * n * n + 2.0 * no * no * nv * nv * n
+    res["mp2_N222_nocc21"] = {"transform_ms": t, "reference_flops": fl, "tflops_reference_equivalent": fl / (t * 1e-3) / 1e12}
     return res
 
 
