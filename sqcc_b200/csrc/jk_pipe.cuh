@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
         const char *pbase = reinterpret_cast<const char *>(p.P);   // running byte pointer: first valid row, sub-row k
         const char *d2row = reinterpret_cast<const char *>(d2p);   // running byte pointer into the D2 tile
         unsigned int poff[R];  // BYTE offsets of the rows relative to pbase (< 4 GB: rows of <= NI adjacent i)
-        bool prv[R];
+        unsigned int prv = 0;  // bit r: row r of the producer's row-block is a stored row of this shard
         double2 xn[R];         // RING == false: the next sub-row's integrals, in flight during the current FMA block
         auto issue_next = [&]() {
             if (prod_kk == kk_hi) {  // advance to the next row-block
@@ -129,20 +129,39 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                 ++prod_rbi;
                 prod_i0 = __shfl_sync(0xffffffffu, my_i0, prod_rbi);
                 prod_j0 = __shfl_sync(0xffffffffu, my_j0, prod_rbi);
-                bool all_valid = true;
+                bool all_valid = (prod_i0 + NI <= n) && (prod_j0 + NJ - 1 <= prod_i0) &&
+                                 pair_index(prod_i0, prod_j0) >= p.ij_begin &&
+                                 pair_index(prod_i0 + NI - 1, prod_j0 + NJ - 1) < p.ij_end;
                 int64_t first = -1;
+                if (all_valid) {
+                    // interior row-block (the common case): row(i,j) = ioff[i] + j Te(i) + Te(j), no per-row tests
+                    prv = (1u << R) - 1u;
+                    int64_t tj[NJ];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int i = prod_i0 + r / NJ, j = prod_j0 + r % NJ;
-                    const int64_t ij = pair_index(i, j);
-                    prv[r] = (i < n) && (j <= i) && ij >= p.ij_begin && ij < p.ij_end;
-                    all_valid = all_valid && prv[r];
-                    int64_t off = 0;
-                    if (prv[r]) {
-                        off = (p.ioff[i] - p.shard_base) + (int64_t)j * subrow_offset(i) + subrow_offset(j);
-                        if (first < 0) first = off;
+                    for (int b = 0; b < NJ; ++b) tj[b] = subrow_offset(prod_j0 + b);
+#pragma unroll
+                    for (int a = 0; a < NI; ++a) {
+                        const int64_t ti = subrow_offset(prod_i0 + a);
+                        const int64_t ra = (p.ioff[prod_i0 + a] - p.shard_base) + (int64_t)prod_j0 * ti;
+                        if (a == 0) first = ra + tj[0];
+#pragma unroll
+                        for (int b = 0; b < NJ; ++b) poff[a * NJ + b] = (unsigned int)((ra + b * ti + tj[b] - first) * 8);
                     }
-                    poff[r] = prv[r] ? (unsigned int)((off - first) * 8) : 0u;
+                } else {
+                    prv = 0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = prod_i0 + r / NJ, j = prod_j0 + r % NJ;
+                        const int64_t ij = pair_index(i, j);
+                        const bool ok = (i < n) && (j <= i) && ij >= p.ij_begin && ij < p.ij_end;
+                        int64_t off = 0;
+                        if (ok) {
+                            prv |= 1u << r;
+                            off = (p.ioff[i] - p.shard_base) + (int64_t)j * subrow_offset(i) + subrow_offset(j);
+                            if (first < 0) first = off;
+                        }
+                        poff[r] = ok ? (unsigned int)((off - first) * 8) : 0u;
+                    }
                 }
                 pbase = reinterpret_cast<const char *>(p.P + (first < 0 ? 0 : first) + l0 + subrow_offset(k0 + kk_lo));
                 d2row = reinterpret_cast<const char *>(d2p + (size_t)kk_lo * ldd);
@@ -157,7 +176,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                     if (prod_mode == 1) on = l0 <= k;
                     if (prod_mode == 2) {
                         const int i = prod_i0 + r / NJ;
-                        const int lmax = !prv[r] ? -1 : (k < i ? k : (k == i ? prod_j0 + r % NJ : -1));
+                        const int lmax = !((prv >> r) & 1u) ? -1 : (k < i ? k : (k == i ? prod_j0 + r % NJ : -1));
                         on = l0 <= lmax;
                     }
                     xn[r] = on ? ldg_stream(reinterpret_cast<const double *>(pbase + poff[r])) : make_double2(0.0, 0.0);
@@ -175,7 +194,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int i = prod_i0 + r / NJ;
-                    const int lmax = !prv[r] ? -1 : (k < i ? k : (k == i ? prod_j0 + r % NJ : -1));
+                    const int lmax = !((prv >> r) & 1u) ? -1 : (k < i ? k : (k == i ? prod_j0 + r % NJ : -1));
                     cp_async16_zfill(dst + r * 512u, pbase + poff[r], l0 <= lmax ? 16u : 0u);
                 }
                 cp_async16_zfill(dst + R * 512u, d2row, lane_in ? 16u : 0u);
