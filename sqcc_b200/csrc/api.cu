@@ -191,7 +191,8 @@ static int row_i(int64_t ij)
 int sqcc_eri_attach(sqcc_ctx *ctx, double *d_native, int n, int64_t ij_begin, int64_t ij_end)
 {
     SQCC_REQUIRE(ctx && d_native, "null ctx / buffer");
-    SQCC_REQUIRE(n > 0 && n <= 4096, "N out of range");
+    // the J/K kernel keeps 32-bit byte offsets between the rows of a 4x4 row-block: 12 i^3 bytes < 2^32
+    SQCC_REQUIRE(n > 0 && n <= 680, "N out of range (1..680: 32-bit row offsets inside a row-block)");
     SQCC_REQUIRE(ij_begin >= 0 && ij_end >= ij_begin && ij_end <= sqcc_npair(n), "bad row range");
     const int a = row_i(ij_begin), b = ij_end > ij_begin ? row_i(ij_end - 1) + 1 : a;
     SQCC_REQUIRE((reinterpret_cast<uintptr_t>(d_native) & 15) == 0, "ERI buffer must be 16-byte aligned");

@@ -284,13 +284,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                 s_w[lane] = rvalid ? __ldg(p.d2 + (size_t)i * ldd + j) : 0.0;
             }
             if (WANTK && lane < JK_KN) {
+                // 32-bit indexing: nspin * n * ldd < 2^31 for every supported n (<= 4096)
                 const int k = (k0 + lane) < n ? (k0 + lane) : n - 1;
+                const double *dk = p.dsp + k;
+                double *su = s_u + lane * (8 * NVP);
 #pragma unroll
                 for (int q = 0; q < NV; ++q) {
                     const int s = q / (NI + NJ), w = q % (NI + NJ);
                     int row = w < NI ? i0 + w : j0 + (w - NI);
                     row = row < n ? row : n - 1;
-                    s_u[lane * (8 * NVP) + q] = __ldg(p.dsp + s * nl + (size_t)row * ldd + k);
+                    su[q] = __ldg(dk + (s * n + row) * ldd);
                 }
             }
             __syncwarp();
