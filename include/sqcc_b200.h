@@ -57,6 +57,16 @@ int64_t sqcc_npair(int n);
 int64_t sqcc_nquad(int n);
 /* Equal-area cut of the row range into `world` contiguous pair-block shards, row granularity. */
 int sqcc_shard_rows(int n, int world, int rank, int64_t *ij_begin, int64_t *ij_end);
+/* Tile-granular shards (the multi-GPU default).  A tile ("pair-block") is a 4 x 4 block of rows (i, j): i-blocks are
+ * anchored at the top of the i range (the last block ends at i = N), j-blocks at multiples of 4; global tile order is
+ * i-block ascending, j-block ascending.  A shard is a contiguous tile range [t_begin, t_end); inside the shard buffer
+ * its rows are stored in pair-index order.  Cutting at tile boundaries keeps every 4 x 4 row-block of the J/K kernel
+ * full on every rank (row-granular cuts leave half-empty blocks at the shard edges: -20 % at 8 ranks, N = 494). */
+int64_t sqcc_tile_count(int n);
+int sqcc_shard_tiles(int n, int world, int rank, int64_t *t_begin, int64_t *t_end);
+/* Rows held by the tile range: for every i the interval [jlo[i], jhi[i]) of j (arrays of N ints). */
+int sqcc_tile_rows(int n, int64_t t_begin, int64_t t_end, int *jlo, int *jhi);
+int64_t sqcc_native_len_tiles(int n, int64_t t_begin, int64_t t_end);
 /* Length in doubles of the native-v1 shard holding rows [ij_begin, ij_end). */
 int64_t sqcc_native_len(int n, int64_t ij_begin, int64_t ij_end);
 /* Offset (doubles, relative to the shard start) of element (i,j,k,l) in native v1; -1 if not canonical. */
@@ -66,6 +76,8 @@ int64_t sqcc_native_offset(int n, int64_t ij_begin, int i, int j, int k, int l);
 /* Attach a caller-owned device buffer of sqcc_native_len(...) doubles as this rank's ERI shard and build
  * the tile schedule.  The buffer must stay alive until detach/destroy. */
 int sqcc_eri_attach(sqcc_ctx *ctx, double *d_native, int n, int64_t ij_begin, int64_t ij_end);
+/* Same for a tile-range shard: buffer of sqcc_native_len_tiles(...) doubles. */
+int sqcc_eri_attach_tiles(sqcc_ctx *ctx, double *d_native, int n, int64_t t_begin, int64_t t_end);
 /* Fill the attached shard with the counter-based synthetic tensor (oracle/synth.py). */
 int sqcc_eri_synth(sqcc_ctx *ctx, uint64_t seed);
 /* Pack a slab ERI[p0:p0+np, :, :, :] of the full tensor (device pointer, [np,N,N,N]) into the shard. */
@@ -80,13 +92,39 @@ int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full);
 /* ---- fused Coulomb/exchange build: replaces hf_ksdft.py:483-495 (RHF/RKS) and :510-535 (UHF/UKS) ----
  * nspin = 1: J = J(D), K = K(D);  nspin = 2: J = J(D[0]+D[1]), K[s] = K(D[s]).
  * want_k = 0 skips exchange (KS-DFT, hf_ksdft.py:488/:517).  One pass over this rank's ERI shard; the
- * outputs are this rank's PARTIAL (already symmetrised) J/K -- sum over ranks gives the full matrices. */
+ * outputs are this rank's PARTIAL (already symmetrised) J/K -- sum over ranks gives the full matrices -- unless a
+ * peer group is attached (sqcc_comm_attach below), in which case they are the full matrices on every rank. */
 int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_J, double *d_K);
 /* Same through host buffers (H2D of D, D2H of J/K inside; stream-synchronous). */
 int sqcc_jk_build_host(sqcc_ctx *ctx, const double *h_D, int nspin, int want_k, double *h_J, double *h_K);
 /* Select the kernel: 0 = cp.async-pipelined warp-task kernel (default), 1 = simple atomics kernel (cross-check),
- * 2 = warp-task kernel with direct 128-bit global loads, 16+c = pipelined kernel with tuning configuration c. */
+ * 2 = warp-task kernel with direct 128-bit global loads (no shared-memory ring), 16+c = tuning configuration c. */
 int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant);
+/* Tuning aid: enable != 0 makes every warp of the pipelined kernel record {start ns, end ns, tasks done}; h_out (optional,
+ * [max_warps][3]) receives the trace of the last launch.  Returns the number of warps written. */
+int sqcc_jk_trace(sqcc_ctx *ctx, int enable, uint64_t *h_out, int max_warps);
+
+/* ---- cross-rank exchange of the partial J/K over NVLink peer memory --------------------------
+ * With a peer group attached, sqcc_jk_build / sqcc_jk_build_host return the FULL J/K on every rank: one kernel per
+ * rank sums the partial accumulators of all ranks through mapped peer memory (reduce-scatter + all-gather in one pass,
+ * fixed summation order -> bit-identical results on all ranks) and symmetrises them into the caller's buffers.
+ * Without a group the outputs are this rank's partials and the caller sums them (e.g. torch.distributed all_reduce).
+ *   multi-process (one process per GPU): after sqcc_eri_attach*, every rank calls sqcc_comm_export, the 64-byte
+ *     handles are all-gathered by the host (torch.distributed), then every rank calls sqcc_comm_attach.
+ *   one process, several contexts: sqcc_comm_attach_local(ctxs, world); contexts on distinct devices then use
+ *     sqcc_jk_build as above; contexts sharing ONE device (tests) must run sqcc_jk_partial on each and finish with a
+ *     single sqcc_jk_reduce_local launch (kernels that wait for each other cannot be separate launches on one GPU).
+ * Every rank of a group must issue the same sequence of builds.  sqcc_comm_status: < 0 after a barrier timeout,
+ * else the group size (0: none). */
+#define SQCC_COMM_HANDLE_BYTES 64
+int sqcc_comm_export(sqcc_ctx *ctx, void *handle /* SQCC_COMM_HANDLE_BYTES */);
+int sqcc_comm_attach(sqcc_ctx *ctx, int world, int rank, const void *handles /* world * SQCC_COMM_HANDLE_BYTES */);
+int sqcc_comm_attach_local(sqcc_ctx **ctxs, int world);
+int sqcc_comm_detach(sqcc_ctx *ctx);
+int sqcc_comm_status(sqcc_ctx *ctx);
+/* prep + fused kernel only: leaves the partial accumulators in the context (no J/K output). */
+int sqcc_jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k);
+int sqcc_jk_reduce_local(sqcc_ctx **ctxs, int world, int nspin, int want_k, double **d_J, double **d_K);
 
 /* ---- LDA exchange grid quadrature: replaces hf_ksdft.py:426-440, :634-646 (rho), ksdft_functional.py
  * :41-65, :68-95, :98-134, :137-177 (v_x, E_x) and hf_ksdft.py:456-461, :469-476 (V_xc) ---- */

@@ -108,3 +108,20 @@ def jk_packed_rows(rows, n, ij0, ij1, d, want_k=True):
     if want_k and d.ndim == 2:
         k = k[0]
     return j, k
+
+
+def jk_packed_segments(n, seed, segments, d, want_k=True):
+    """Partial J/K of a shard given as a list of canonical row ranges [(ij0, ij1), ...] of the synthetic tensor
+    (a tile-range shard of sqcc_shard_tiles is a union of such runs)."""
+    nspin = 1 if d.ndim == 2 else 2
+    j = np.zeros((n, n))
+    k = np.zeros((nspin, n, n)) if want_k else None
+    for ij0, ij1 in segments:
+        rows = synth_rows(n, seed, ij0, ij1)
+        jp, kp = jk_packed_rows(rows, n, ij0, ij1, d, want_k)
+        j += jp
+        if want_k:
+            k += kp if d.ndim == 3 else kp[None]
+    if want_k and d.ndim == 2:
+        k = k[0]
+    return j, k

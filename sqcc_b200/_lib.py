@@ -21,9 +21,14 @@ SIGNATURES = {
     "sqcc_npair": (c_i64, [c_int]),
     "sqcc_nquad": (c_i64, [c_int]),
     "sqcc_shard_rows": (c_int, [c_int, c_int, c_int, c_i64_p, c_i64_p]),
+    "sqcc_tile_count": (c_i64, [c_int]),
+    "sqcc_shard_tiles": (c_int, [c_int, c_int, c_int, c_i64_p, c_i64_p]),
+    "sqcc_tile_rows": (c_int, [c_int, c_i64, c_i64, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "sqcc_native_len_tiles": (c_i64, [c_int, c_i64, c_i64]),
     "sqcc_native_len": (c_i64, [c_int, c_i64, c_i64]),
     "sqcc_native_offset": (c_i64, [c_int, c_i64, c_int, c_int, c_int, c_int]),
     "sqcc_eri_attach": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_i64]),
+    "sqcc_eri_attach_tiles": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_i64]),
     "sqcc_eri_synth": (c_int, [c_void_p, c_u64]),
     "sqcc_eri_pack_full_slab": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "sqcc_eri_pack_full_host": (c_int, [c_void_p, c_void_p]),
@@ -32,6 +37,14 @@ SIGNATURES = {
     "sqcc_jk_build": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sqcc_jk_build_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sqcc_jk_set_variant": (c_int, [c_void_p, c_int]),
+    "sqcc_comm_export": (c_int, [c_void_p, c_void_p]),
+    "sqcc_comm_attach": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "sqcc_comm_attach_local": (c_int, [ctypes.POINTER(c_void_p), c_int]),
+    "sqcc_comm_detach": (c_int, [c_void_p]),
+    "sqcc_comm_status": (c_int, [c_void_p]),
+    "sqcc_jk_partial": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "sqcc_jk_reduce_local": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
+    "sqcc_jk_trace": (c_int, [c_void_p, c_int, c_void_p, c_int]),
     "sqcc_grid_attach": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int]),
     "sqcc_lda_vxc": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "sqcc_lda_vxc_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -14,20 +14,41 @@ from . import _lib
 
 
 class ShardPlan:
-    """Equal-area cut of the packed rows over `world` ranks (pure host arithmetic, no GPU needed)."""
+    """Equal-area cut of the packed tensor over `world` ranks at 4 x 4 pair-block ("tile") granularity
+    (include/sqcc_b200.h: sqcc_shard_tiles; pure host arithmetic, no GPU needed).
+
+    Rank r holds the tile range [t_begin, t_end); `jlo`/`jhi` give, per i, the interval of j whose rows (i, j)
+    it stores (pair-index order inside the shard buffer)."""
 
     def __init__(self, n, world=1, rank=0):
         lib = _lib.load()
         self.n, self.world, self.rank = int(n), int(world), int(rank)
         b, e = ctypes.c_int64(), ctypes.c_int64()
-        _lib.check(lib.sqcc_shard_rows(self.n, self.world, self.rank, ctypes.byref(b), ctypes.byref(e)))
-        self.ij_begin, self.ij_end = b.value, e.value
-        self.native_len = lib.sqcc_native_len(self.n, self.ij_begin, self.ij_end)
+        _lib.check(lib.sqcc_shard_tiles(self.n, self.world, self.rank, ctypes.byref(b), ctypes.byref(e)))
+        self.t_begin, self.t_end = b.value, e.value
+        self.native_len = lib.sqcc_native_len_tiles(self.n, self.t_begin, self.t_end)
         if self.native_len < 0:
             raise _lib.SqccError("invalid shard")
-        # first / one-past-last i of rows (i, *) held by this rank
-        self.i_begin = int((np.sqrt(8.0 * self.ij_begin + 1.0) - 1.0) / 2.0 + 0.5)
-        self.i_end = int((np.sqrt(8.0 * self.ij_end + 1.0) - 1.0) / 2.0 + 0.5)
+        lo, hi = (ctypes.c_int * self.n)(), (ctypes.c_int * self.n)()
+        _lib.check(lib.sqcc_tile_rows(self.n, self.t_begin, self.t_end, lo, hi))
+        self.jlo, self.jhi = np.array(lo[:], dtype=np.int64), np.array(hi[:], dtype=np.int64)
+        held = np.nonzero(self.jhi > self.jlo)[0]
+        # first / one-past-last i with held rows
+        self.i_begin, self.i_end = (int(held[0]), int(held[-1]) + 1) if held.size else (0, 0)
+        self.nrows = int((self.jhi - self.jlo).sum())
+
+    def segments(self):
+        """Maximal runs [ij_lo, ij_hi) of consecutive pair indices held by this rank (canonical row ranges)."""
+        segs = []
+        for i in range(self.n):
+            if self.jhi[i] > self.jlo[i]:
+                a = i * (i + 1) // 2 + int(self.jlo[i])
+                b = i * (i + 1) // 2 + int(self.jhi[i])
+                if segs and segs[-1][1] == a:
+                    segs[-1][1] = b
+                else:
+                    segs.append([a, b])
+        return [tuple(x) for x in segs]
 
     @staticmethod
     def all_cuts(n, world):
@@ -49,8 +70,15 @@ def _ptr(t):
 class FockEngine:
     """J/K, LDA grid quadrature and MP2 transforms on one B200; mirrors the loop nests of hf_ksdft.py/mp2.py."""
 
-    def __init__(self, device=None, rank=0, world=1, group=None):
+    def __init__(self, device=None, rank=0, world=1, group=None, exchange="p2p"):
+        """exchange: how the partial [J; K] of the ranks are summed when a process group is initialised --
+        "p2p"  one fused kernel per rank over NVLink peer memory (csrc/comm.cu; the default),
+        "nccl" finalize + ``dist.all_reduce`` (the baseline the fused exchange is measured against)."""
         self.lib = _lib.load()
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.exchange = exchange
+        self._p2p = False
         if not torch.cuda.is_available():
             raise _lib.SqccError("sqcc_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
@@ -69,8 +97,18 @@ class FockEngine:
             s = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.sqcc_ctx_set_stream(self.ctx, ctypes.c_void_p(s)))
 
+    def _detach_peers(self):
+        """Unmap the peers' regions; nobody may free its region before every rank has unmapped it."""
+        if self._p2p:
+            self._p2p = False
+            self.lib.sqcc_comm_detach(self.ctx)
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier(group=self.group)
+
     def close(self):
         if getattr(self, "ctx", None):
+            self._detach_peers()
             self.lib.sqcc_ctx_destroy(self.ctx)
             self.ctx = None
 
@@ -82,11 +120,36 @@ class FockEngine:
 
     # ------------------------------------------------------------------ ERI ingest
     def _alloc_shard(self, n):
+        self._detach_peers()
         self.n = int(n)
         self.plan = ShardPlan(n, self.world, self.rank)
         self.eri = torch.empty(max(self.plan.native_len, 2), dtype=torch.float64, device=self.device)
         self._use_stream()
-        _lib.check(self.lib.sqcc_eri_attach(self.ctx, _ptr(self.eri), self.n, self.plan.ij_begin, self.plan.ij_end))
+        _lib.check(self.lib.sqcc_eri_attach_tiles(self.ctx, _ptr(self.eri), self.n, self.plan.t_begin, self.plan.t_end))
+        self._p2p = False
+        if self.exchange == "p2p" and self._group_size() > 1:
+            self._attach_peers()
+
+    def _group_size(self):
+        import torch.distributed as dist
+        if self.world > 1 and dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group)
+        return 1
+
+    def _attach_peers(self):
+        """Exchange the CUDA IPC handles of the ranks' accumulator regions (torch.distributed is only the
+        messenger) and map them: afterwards sqcc_jk_build returns the full J/K on every rank."""
+        import torch.distributed as dist
+        nb = 64  # SQCC_COMM_HANDLE_BYTES
+        mine = (ctypes.c_ubyte * nb)()
+        _lib.check(self.lib.sqcc_comm_export(self.ctx, mine))
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+        gathered = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(gathered, t, group=self.group)
+        blob = bytes(torch.cat(gathered).cpu().numpy().tobytes())
+        _lib.check(self.lib.sqcc_comm_attach(self.ctx, self.world, self.rank, blob))
+        dist.barrier(group=self.group)
+        self._p2p = True
 
     def attach_eri_synth(self, n, seed):
         """Counter-based synthetic packed ERI, generated on the device shard by shard."""
@@ -107,18 +170,18 @@ class FockEngine:
         """Pack a canonical packed host vector (ij(ij+1)/2+kl) into this rank's shard."""
         packed = np.ascontiguousarray(packed, dtype=np.float64)
         self._alloc_shard(n)
-        lo, hi = self.plan.ij_begin, self.plan.ij_end
         budget = 64 << 20  # doubles per staged chunk
-        ij = lo
-        while ij < hi:
-            e = ij
-            while e < hi and (e + 1) * (e + 2) // 2 - ij * (ij + 1) // 2 <= budget:
-                e += 1
-            e = max(e, ij + 1)
-            seg = torch.from_numpy(packed[ij * (ij + 1) // 2: e * (e + 1) // 2]).to(self.device)
-            _lib.check(self.lib.sqcc_eri_pack_canonical(self.ctx, _ptr(seg), ij, e - ij))
-            torch.cuda.current_stream().synchronize()
-            ij = e
+        for lo, hi in self.plan.segments():
+            ij = lo
+            while ij < hi:
+                e = ij
+                while e < hi and (e + 1) * (e + 2) // 2 - ij * (ij + 1) // 2 <= budget:
+                    e += 1
+                e = max(e, ij + 1)
+                seg = torch.from_numpy(packed[ij * (ij + 1) // 2: e * (e + 1) // 2]).to(self.device)
+                _lib.check(self.lib.sqcc_eri_pack_canonical(self.ctx, _ptr(seg), ij, e - ij))
+                torch.cuda.current_stream().synchronize()
+                ij = e
         return self
 
     def eri_bytes(self):
@@ -146,8 +209,13 @@ class FockEngine:
         self._use_stream()
         _lib.check(self.lib.sqcc_jk_build(self.ctx, _ptr(d), nspin, int(want_k), _ptr(out[0]),
                                           _ptr(out[1]) if want_k else None))
-        reduce_partials(out, self.group)
+        if not self._p2p:
+            reduce_partials(out, self.group)
         return out
+
+    def comm_check(self):
+        """Raises if a peer barrier of the fused exchange timed out (reads a mapped host word; no sync)."""
+        return _lib.check(self.lib.sqcc_comm_status(self.ctx))
 
     def jk(self, d, want_k=True):
         """Host in / host out, reference semantics (hf_ksdft.py:483-495, :510-535).
@@ -157,13 +225,15 @@ class FockEngine:
         d = np.ascontiguousarray(d, dtype=np.float64)
         nspin = 1 if d.ndim == 2 else 2
         n = self.n
-        if self.world == 1:
+        if self.world == 1 or self._p2p:
             j = np.empty((n, n))
             k = np.empty((nspin, n, n)) if want_k else None
             self._use_stream()
             _lib.check(self.lib.sqcc_jk_build_host(
                 self.ctx, d.ctypes.data_as(ctypes.c_void_p), nspin, int(want_k),
                 j.ctypes.data_as(ctypes.c_void_p), k.ctypes.data_as(ctypes.c_void_p) if want_k else None))
+            if self._p2p:
+                self.comm_check()
         else:
             out = self.jk_device(torch.from_numpy(d).to(self.device), want_k).cpu().numpy()
             j, k = out[0], (out[1:] if want_k else None)
@@ -252,3 +322,57 @@ class FockEngine:
 
     def synchronize(self):
         _lib.check(self.lib.sqcc_ctx_synchronize(self.ctx))
+
+
+class FockGroup:
+    """Several shard contexts driven by ONE process: one engine per rank, on distinct devices
+    or -- for single-GPU tests of the exchange -- all on the same device.  The partial J/K of the ranks are summed by
+    the fused peer-memory kernel (csrc/comm.cu); with a shared device that is a single launch covering all ranks."""
+
+    def __init__(self, devices):
+        self.engines = [FockEngine(device=d, rank=r, world=len(devices), exchange="nccl") for r, d in enumerate(devices)]
+        self.world = len(devices)
+        self.same_device = len(set(int(d) for d in devices)) == 1
+        self.lib = self.engines[0].lib
+
+    def attach_eri_synth(self, n, seed):
+        for e in self.engines:
+            e.attach_eri_synth(n, seed)
+        arr = (ctypes.c_void_p * self.world)(*[e.ctx for e in self.engines])
+        _lib.check(self.lib.sqcc_comm_attach_local(arr, self.world))
+        return self
+
+    def jk_device(self, d_host, want_k=True):
+        """d_host: numpy [N,N] or [2,N,N].  Returns one stacked device buffer [J; K...] per rank (all identical)."""
+        d_host = np.ascontiguousarray(d_host, dtype=np.float64)
+        nspin = 1 if d_host.ndim == 2 else 2
+        n = self.engines[0].n
+        outs, ds = [], []
+        for e in self.engines:
+            with torch.cuda.device(e.device):
+                ds.append(torch.from_numpy(d_host).to(e.device))
+                outs.append(torch.empty((1 + (nspin if want_k else 0), n, n), dtype=torch.float64, device=e.device))
+        if self.same_device:
+            for e, d in zip(self.engines, ds):
+                e._use_stream()
+                _lib.check(self.lib.sqcc_jk_partial(e.ctx, _ptr(d), nspin, int(want_k)))
+            ctxs = (ctypes.c_void_p * self.world)(*[e.ctx for e in self.engines])
+            js = (ctypes.c_void_p * self.world)(*[o[0].data_ptr() for o in outs])
+            ks = (ctypes.c_void_p * self.world)(*[(o[1].data_ptr() if want_k else None) for o in outs])
+            _lib.check(self.lib.sqcc_jk_reduce_local(ctxs, self.world, nspin, int(want_k), js, ks))
+        else:
+            for e, d, o in zip(self.engines, ds, outs):
+                with torch.cuda.device(e.device):
+                    e._use_stream()
+                    _lib.check(self.lib.sqcc_jk_build(e.ctx, _ptr(d), nspin, int(want_k), _ptr(o[0]),
+                                                      _ptr(o[1]) if want_k else None))
+        for e in self.engines:
+            e.synchronize()
+            e.comm_check()
+        return outs
+
+    def close(self):
+        for e in self.engines:
+            self.lib.sqcc_comm_detach(e.ctx)
+        for e in self.engines:
+            e.close()

@@ -1,5 +1,6 @@
 // C ABI of libsqcc_b200.so (see include/sqcc_b200.h).  Thin: argument checks, staging, dispatch.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -77,6 +78,57 @@ static int64_t shard_cut(int n, int world, int g)
     return lo;
 }
 
+// Tile index at which shard g of `world` starts: equal-COST cut with 4 x 4 tile granularity.  The cost of a row is its
+// native length times (1 + alpha / (i + 1)): short rows spend relatively more warp tasks on the triangular edge
+// (l <= k masking) of the sub-rows, measured as ~8 % lower streaming rate for the i < 294 shard of N = 494 (alpha = 40).
+static double shard_alpha()
+{
+    if (const char *e = getenv("SQCC_SHARD_ALPHA")) return atof(e);
+    return 40.0;
+}
+
+static int64_t tile_cut(int n, int world, int g)
+{
+    const int64_t nt = tile_count(n);
+    if (g <= 0) return 0;
+    if (g >= world) return nt;
+    // cumulative native length by tile (tile order: i-block ascending, j-block ascending)
+    std::vector<double> cum;
+    cum.reserve(nt + 1);
+    cum.push_back(0.0);
+    const double alpha = shard_alpha();
+    const int nb = (n + 3) / 4;
+    for (int b = 0; b < nb; ++b) {
+        int lo = n - 4 * (nb - b), hi = lo + 4;
+        if (lo < 0) lo = 0;
+        for (int j0 = 0; j0 <= hi - 1; j0 += 4) {
+            double cost = 0.0;
+            for (int i = lo; i < hi; ++i)
+                for (int j = j0; j < j0 + 4 && j <= i; ++j) cost += (double)row_length(i, j) * (1.0 + alpha / (i + 1.0));
+            cum.push_back(cum.back() + cost);
+        }
+    }
+    const double target = cum.back() * (double)g / (double)world;
+    int64_t lo = 0, hi = nt;
+    while (lo < hi) {  // first tile whose start cost >= target
+        int64_t mid = (lo + hi) / 2;
+        if (cum[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+static int attach_common(sqcc_ctx *ctx, double *d_native, int n)
+{
+    SQCC_REQUIRE((reinterpret_cast<uintptr_t>(d_native) & 15) == 0, "ERI buffer must be 16-byte aligned");
+    SQCC_CUDA(cudaSetDevice(ctx->device));
+    ctx->d_eri = d_native;
+    ctx->n = n;
+    ctx->ldd = (n + 3) & ~3;
+    SQCC_TRY(eri_build_tables(ctx));
+    SQCC_TRY(jk_build_schedule(ctx));
+    return SQCC_OK;
+}
+
 }  // namespace sqcc
 
 using namespace sqcc;
@@ -121,8 +173,9 @@ int sqcc_ctx_destroy(sqcc_ctx *ctx)
         cudaFree(sc.d_tasks);
     }
     cudaFree(ctx->d_dwork);
-    cudaFree(ctx->d_acc);
+    comm_free(ctx);
     cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_trace);
     cudaFree(ctx->d_io);
     cudaFree(ctx->d_gridwork);
     cudaFree(ctx->d_mp2work);
@@ -167,6 +220,38 @@ int sqcc_shard_rows(int n, int world, int rank, int64_t *ij_begin, int64_t *ij_e
     return SQCC_OK;
 }
 
+int64_t sqcc_tile_count(int n) { return n > 0 ? tile_count(n) : -1; }
+
+int sqcc_shard_tiles(int n, int world, int rank, int64_t *t_begin, int64_t *t_end)
+{
+    SQCC_REQUIRE(n > 0 && world > 0 && rank >= 0 && rank < world && t_begin && t_end, "bad shard arguments");
+    int64_t a = tile_cut(n, world, rank), b = tile_cut(n, world, rank + 1);
+    if (b < a) b = a;
+    *t_begin = a;
+    *t_end = b;
+    return SQCC_OK;
+}
+
+int sqcc_tile_rows(int n, int64_t t_begin, int64_t t_end, int *jlo, int *jhi)
+{
+    SQCC_REQUIRE(n > 0 && t_begin >= 0 && t_end >= t_begin && t_end <= tile_count(n) && jlo && jhi, "bad tile range");
+    std::vector<int> a, b;
+    tile_intervals(n, t_begin, t_end, a, b);
+    for (int i = 0; i < n; ++i) {
+        jlo[i] = a[i];
+        jhi[i] = b[i];
+    }
+    return SQCC_OK;
+}
+
+int64_t sqcc_native_len_tiles(int n, int64_t t_begin, int64_t t_end)
+{
+    if (n <= 0 || t_begin < 0 || t_end < t_begin || t_end > tile_count(n)) return -1;
+    std::vector<int> a, b;
+    tile_intervals(n, t_begin, t_end, a, b);
+    return intervals_native_len(n, a, b);
+}
+
 int64_t sqcc_native_len(int n, int64_t ij_begin, int64_t ij_end)
 {
     if (n <= 0 || ij_begin < 0 || ij_end < ij_begin || ij_end > sqcc_npair(n)) return -1;
@@ -180,33 +265,23 @@ int64_t sqcc_native_offset(int n, int64_t ij_begin, int i, int j, int k, int l)
     return global_row_offset(pair_index(i, j)) - global_row_offset(ij_begin) + subrow_offset(k) + l;
 }
 
-static int row_i(int64_t ij)
-{
-    int64_t t = (int64_t)((sqrt(8.0 * (double)ij + 1.0) - 1.0) * 0.5);
-    while (t * (t + 1) / 2 > ij) --t;
-    while ((t + 1) * (t + 2) / 2 <= ij) ++t;
-    return (int)t;
-}
-
 int sqcc_eri_attach(sqcc_ctx *ctx, double *d_native, int n, int64_t ij_begin, int64_t ij_end)
 {
     SQCC_REQUIRE(ctx && d_native, "null ctx / buffer");
     // the J/K kernel keeps 32-bit byte offsets between the rows of a 4x4 row-block: 12 i^3 bytes < 2^32
     SQCC_REQUIRE(n > 0 && n <= 680, "N out of range (1..680: 32-bit row offsets inside a row-block)");
     SQCC_REQUIRE(ij_begin >= 0 && ij_end >= ij_begin && ij_end <= sqcc_npair(n), "bad row range");
-    const int a = row_i(ij_begin), b = ij_end > ij_begin ? row_i(ij_end - 1) + 1 : a;
-    SQCC_REQUIRE((reinterpret_cast<uintptr_t>(d_native) & 15) == 0, "ERI buffer must be 16-byte aligned");
-    SQCC_CUDA(cudaSetDevice(ctx->device));
-    ctx->d_eri = d_native;
-    ctx->n = n;
-    ctx->ldd = (n + 3) & ~3;
-    ctx->ij_begin = ij_begin;
-    ctx->ij_end = ij_end;
-    ctx->i_begin = a;
-    ctx->i_end = b;
-    SQCC_TRY(eri_build_tables(ctx));
-    SQCC_TRY(jk_build_schedule(ctx));
-    return SQCC_OK;
+    row_intervals(n, ij_begin, ij_end, ctx->jlo, ctx->jhi);
+    return attach_common(ctx, d_native, n);
+}
+
+int sqcc_eri_attach_tiles(sqcc_ctx *ctx, double *d_native, int n, int64_t t_begin, int64_t t_end)
+{
+    SQCC_REQUIRE(ctx && d_native, "null ctx / buffer");
+    SQCC_REQUIRE(n > 0 && n <= 680, "N out of range (1..680: 32-bit row offsets inside a row-block)");
+    SQCC_REQUIRE(t_begin >= 0 && t_end >= t_begin && t_end <= tile_count(n), "bad tile range");
+    tile_intervals(n, t_begin, t_end, ctx->jlo, ctx->jhi);
+    return attach_common(ctx, d_native, n);
 }
 
 int sqcc_eri_synth(sqcc_ctx *ctx, uint64_t seed)
@@ -238,7 +313,7 @@ int sqcc_eri_pack_full_host(sqcc_ctx *ctx, const double *h_eri_full)
     SQCC_CUDA(cudaEventCreate(&done[0]));
     SQCC_CUDA(cudaEventCreate(&done[1]));
     int buf = 0, issued = 0;
-    for (int p0 = ctx->i_begin; p0 < ctx->i_end; p0 += np, buf ^= 1, ++issued) {
+    for (int p0 = ctx->i_begin; p0 < ctx->i_end; p0 += np, buf ^= 1, ++issued) {   // slabs without held rows pack nothing
         int cnt = p0 + np <= ctx->i_end ? np : ctx->i_end - p0;
         double *hp = ctx->h_pin + (size_t)buf * slab * np;
         double *dp = ctx->d_io + (size_t)buf * slab * np;
@@ -274,6 +349,28 @@ int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant)
     ctx->jk_variant = variant < 16 ? variant : 0;
     ctx->jk_cfg = variant >= 16 ? variant - 16 : 0;
     return SQCC_OK;
+}
+
+int sqcc_jk_trace(sqcc_ctx *ctx, int enable, uint64_t *h_out, int max_warps)
+{
+    SQCC_REQUIRE(ctx, "null ctx");
+    constexpr int CAP = 148 * 4 * 16;   // warps of the largest persistent grid
+    if (enable && !ctx->d_trace) {
+        SQCC_CUDA(cudaMalloc(&ctx->d_trace, sizeof(unsigned long long) * 3 * CAP));
+        SQCC_CUDA(cudaMemset(ctx->d_trace, 0, sizeof(unsigned long long) * 3 * CAP));
+    }
+    int nw = 0;
+    if (h_out && ctx->d_trace) {
+        nw = ctx->trace_warps < max_warps ? ctx->trace_warps : max_warps;
+        SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+        SQCC_CUDA(cudaMemcpy(h_out, ctx->d_trace, sizeof(unsigned long long) * 3 * nw, cudaMemcpyDeviceToHost));
+    }
+    if (!enable && ctx->d_trace) {
+        SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_trace);
+        ctx->d_trace = nullptr;
+    }
+    return nw;
 }
 
 int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_J, double *d_K)

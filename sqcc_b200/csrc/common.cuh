@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -66,6 +67,8 @@ constexpr int JK_NJ = 2;       // rows j per row-block
 
 struct RowBlock {
     int i0, j0;
+    unsigned int mask;   // bit a*NJ+b: row (i0+a, j0+b) is held by this shard
+    int pad;
 };
 struct JKTask {
     int k0;        // first k of the range (multiple of JK_KN)
@@ -82,6 +85,25 @@ struct JKSchedule {
     int n_tasks = 0;
 };
 
+// Peer group of the fused J/K exchange (comm.cu)
+constexpr int COMM_MAXW = 16;
+struct CommRank;
+struct Comm {
+    int world = 1, rank = 0;
+    bool attached = false;      // peer_base[0..world) are valid
+    bool ipc = false;           // peers were opened with cudaIpcOpenMemHandle (other processes)
+    bool same_device = false;   // in-process group whose contexts share one device (single-launch emulation)
+    double *d_sym = nullptr;    // symmetric region [acc 3 nl][res 3 nl][flags 2 COMM_MAXW u64]
+    void *peer_base[COMM_MAXW] = {};
+    unsigned long long epoch = 0;
+    unsigned int bar_count = 0;
+    unsigned int *d_gridbar = nullptr;
+    CommRank *d_view = nullptr;  // [COMM_MAXW]
+    bool view_valid = false;     // d_view[0] holds this rank's view for outputs (view_J, view_K)
+    double *view_J = nullptr, *view_K = nullptr;
+    int *h_status = nullptr, *d_status = nullptr;   // mapped host word
+};
+
 struct Timer {
     cudaEvent_t a = nullptr, b = nullptr;
     bool used = false;
@@ -95,25 +117,34 @@ struct sqcc_ctx {
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
 
-    // ERI shard (caller-owned)
+    // ERI shard (caller-owned).  A shard holds, for every i, the rows (i, j) with j in [jlo[i], jhi[i]) -- stored in
+    // pair-index order.  Row-range shards [ij_begin, ij_end) and tile-range shards (sqcc_shard_tiles) are both
+    // expressed this way.
     double *d_eri = nullptr;
     int n = 0;
     int ldd = 0;  // padded leading dimension of the D/J~/K~ work matrices (multiple of 4)
-    int64_t ij_begin = 0, ij_end = 0;
-    int i_begin = 0, i_end = 0;  // i range covered by the shard (rows (i, *))
+    std::vector<int> jlo, jhi;   // [n] held j interval per i (empty: jlo == jhi)
+    std::vector<int64_t> h_rowptr;  // [n + 1] number of held rows with i' < i
+    std::vector<int64_t> h_ioff;    // [n] local offset such that row (i,j) starts at h_ioff[i] + j Te(i) + Te(j)
+    int64_t nrows = 0;           // held rows
+    bool whole = false;          // every row of the tensor is held (unsharded)
+    int i_begin = 0, i_end = 0;  // i range with held rows
     int64_t native_len = 0;
     int64_t n_unique = 0;
-    int64_t *d_rowoff = nullptr;  // [npair_local + 1] offsets relative to shard start
-    int64_t *d_ioff = nullptr;    // [n + 1] offsets of rows (i,0) in the full native tensor
-    int64_t shard_base = 0;       // offset of the shard's first row in the full native tensor
+    int64_t *d_rowoff = nullptr;  // [nrows + 1] offsets of the held rows relative to the shard start
+    int64_t *d_rowij = nullptr;   // [nrows] global pair index of the held rows
+    int64_t *d_ioff = nullptr;    // [n] device copy of h_ioff
     sqcc::JKSchedule sched[3];    // row-block shapes [0]: 4x2 (RHF, J-only)  [1]: 2x2 (UHF)  [2]: 4x4 (tuning)
     int jk_variant = 0;
     int jk_cfg = 0;  // tuning knob of the pipelined kernel (warps, stages), see launch_pipe
 
     // J/K scratch
     double *d_dwork = nullptr;   // [3][N][ldd]: D2 = 2*(Da+Db), Da, Db (padded)
-    double *d_acc = nullptr;     // [3][N][ldd]: J~, K~a, K~b
+    double *d_acc = nullptr;     // [3][N][ldd]: J~, K~a, K~b (first part of comm.d_sym)
+    sqcc::Comm comm;
     unsigned int *d_counter = nullptr;
+    unsigned long long *d_trace = nullptr;  // tuning: per-warp task trace of the last pipelined J/K launch (sqcc_jk_trace)
+    int trace_warps = 0;
     double *d_io = nullptr;      // device staging for *_host calls
     size_t io_bytes = 0;
     double *h_pin = nullptr;     // pinned staging
@@ -143,6 +174,11 @@ int timer_start(sqcc_ctx *ctx, int slot);
 int timer_stop(sqcc_ctx *ctx, int slot);
 
 // eri_layout.cu
+void pair_unrank_host(int64_t ij, int &i, int &j);
+int64_t tile_count(int n);
+int tile_intervals(int n, int64_t t_begin, int64_t t_end, std::vector<int> &jlo, std::vector<int> &jhi);
+int row_intervals(int n, int64_t ij_begin, int64_t ij_end, std::vector<int> &jlo, std::vector<int> &jhi);
+int64_t intervals_native_len(int n, const std::vector<int> &jlo, const std::vector<int> &jhi);
 int eri_build_tables(sqcc_ctx *ctx);
 int eri_synth(sqcc_ctx *ctx, uint64_t seed);
 int eri_pack_full_slab(sqcc_ctx *ctx, const double *d_slab, int p0, int np);
@@ -151,7 +187,13 @@ int eri_unpack_full(sqcc_ctx *ctx, double *d_full);
 
 // jk_fused.cu
 int jk_build_schedule(sqcc_ctx *ctx);
+int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k);
 int jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_J, double *d_K);
+
+// comm.cu
+int comm_alloc(sqcc_ctx *ctx);
+void comm_free(sqcc_ctx *ctx);
+int jk_reduce(sqcc_ctx *ctx, int nspin, int want_k, double *d_J, double *d_K);
 
 // grid_lda.cu
 int lda_vxc(sqcc_ctx *ctx, const double *d_D, int nspin, double *d_Vxc, double *d_Exc, double *d_rho);

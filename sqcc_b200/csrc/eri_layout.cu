@@ -23,28 +23,141 @@ __host__ __device__ __forceinline__ void pair_unrank(int64_t ij, int &i, int &j)
     j = (int)(ij - t * (t + 1) / 2);
 }
 
+void pair_unrank_host(int64_t ij, int &i, int &j) { pair_unrank(ij, i, j); }
+
+// ---- shard geometry (host) ---------------------------------------------------------------------------
+// Tiles ("pair-blocks"): 4 x 4 blocks of rows (i, j).  The i-blocks are anchored at the TOP of the i range
+// (block b covers i in [n - 4 (NB - b), n - 4 (NB - b - 1)) clipped to >= 0), so that the longest rows always sit in
+// full blocks; j-blocks start at multiples of 4.  Global tile order: i-block ascending, j-block ascending.
+static inline void iblock_range(int n, int b, int &lo, int &hi)
+{
+    const int nb = (n + 3) / 4;
+    lo = n - 4 * (nb - b);
+    hi = lo + 4;
+    if (lo < 0) lo = 0;
+}
+
+int64_t tile_count(int n)
+{
+    const int nb = (n + 3) / 4;
+    int64_t t = 0;
+    for (int b = 0; b < nb; ++b) {
+        int lo, hi;
+        iblock_range(n, b, lo, hi);
+        t += (hi - 1) / 4 + 1;
+    }
+    return t;
+}
+
+int tile_intervals(int n, int64_t t_begin, int64_t t_end, std::vector<int> &jlo, std::vector<int> &jhi)
+{
+    jlo.assign(n, 0);
+    jhi.assign(n, 0);
+    const int nb = (n + 3) / 4;
+    int64_t t0 = 0;
+    for (int b = 0; b < nb; ++b) {
+        int lo, hi;
+        iblock_range(n, b, lo, hi);
+        const int64_t cnt = (hi - 1) / 4 + 1;
+        const int64_t a = t_begin > t0 ? t_begin - t0 : 0, c = (t_end < t0 + cnt ? t_end : t0 + cnt) - t0;
+        if (c > a) {
+            for (int i = lo; i < hi; ++i) {
+                jlo[i] = (int)(4 * a < i + 1 ? 4 * a : i + 1);
+                jhi[i] = (int)(4 * c < i + 1 ? 4 * c : i + 1);
+            }
+        }
+        t0 += cnt;
+    }
+    return SQCC_OK;
+}
+
+int row_intervals(int n, int64_t ij_begin, int64_t ij_end, std::vector<int> &jlo, std::vector<int> &jhi)
+{
+    jlo.assign(n, 0);
+    jhi.assign(n, 0);
+    for (int i = 0; i < n; ++i) {
+        const int64_t r0 = pair_index(i, 0), r1 = r0 + i + 1;
+        const int64_t a = ij_begin > r0 ? ij_begin : r0, c = ij_end < r1 ? ij_end : r1;
+        if (c > a) {
+            jlo[i] = (int)(a - r0);
+            jhi[i] = (int)(c - r0);
+        }
+    }
+    return SQCC_OK;
+}
+
+int64_t intervals_native_len(int n, const std::vector<int> &jlo, const std::vector<int> &jhi)
+{
+    int64_t len = 0;
+    for (int i = 0; i < n; ++i)
+        if (jhi[i] > jlo[i]) len += (int64_t)(jhi[i] - jlo[i]) * subrow_offset(i) + subrow_offset(jhi[i]) - subrow_offset(jlo[i]);
+    return len;
+}
+
 int eri_build_tables(sqcc_ctx *ctx)
 {
-    int64_t nrows = ctx->ij_end - ctx->ij_begin;
-    std::vector<int64_t> h(nrows + 1);
-    int i, j;
-    pair_unrank(ctx->ij_begin, i, j);
-    int64_t off = 0, uniq = 0;
-    for (int64_t r = 0; r < nrows; ++r) {
-        h[r] = off;
-        off += row_length(i, j);
-        uniq += pair_index(i, j) + 1;
-        if (++j > i) { ++i; j = 0; }
+    const int n = ctx->n;
+    ctx->h_rowptr.assign(n + 1, 0);
+    ctx->h_ioff.assign(n, 0);
+    ctx->i_begin = n;
+    ctx->i_end = 0;
+    for (int i = 0; i < n; ++i) {
+        ctx->h_rowptr[i + 1] = ctx->h_rowptr[i] + (ctx->jhi[i] - ctx->jlo[i]);
+        if (ctx->jhi[i] > ctx->jlo[i]) {
+            if (i < ctx->i_begin) ctx->i_begin = i;
+            ctx->i_end = i + 1;
+        }
+    }
+    if (ctx->i_end == 0) ctx->i_begin = 0;
+    const int64_t nrows = ctx->h_rowptr[n];
+    ctx->nrows = nrows;
+    ctx->whole = nrows == pair_index(n, 0);
+    std::vector<int64_t> h(nrows + 1), hij(nrows > 0 ? nrows : 1);
+    int64_t off = 0, uniq = 0, r = 0;
+    for (int i = 0; i < n; ++i) {
+        if (ctx->jhi[i] > ctx->jlo[i])
+            ctx->h_ioff[i] = off - ((int64_t)ctx->jlo[i] * subrow_offset(i) + subrow_offset(ctx->jlo[i]));
+        for (int j = ctx->jlo[i]; j < ctx->jhi[i]; ++j, ++r) {
+            h[r] = off;
+            hij[r] = pair_index(i, j);
+            off += row_length(i, j);
+            uniq += pair_index(i, j) + 1;
+        }
     }
     h[nrows] = off;
     ctx->native_len = off;
     ctx->n_unique = uniq;
     if (ctx->d_rowoff) cudaFree(ctx->d_rowoff);
+    if (ctx->d_rowij) cudaFree(ctx->d_rowij);
+    if (ctx->d_ioff) cudaFree(ctx->d_ioff);
+    ctx->d_rowoff = ctx->d_rowij = ctx->d_ioff = nullptr;
     SQCC_CUDA(cudaMalloc(&ctx->d_rowoff, sizeof(int64_t) * (nrows + 1)));
+    SQCC_CUDA(cudaMalloc(&ctx->d_rowij, sizeof(int64_t) * hij.size()));
+    SQCC_CUDA(cudaMalloc(&ctx->d_ioff, sizeof(int64_t) * n));
     SQCC_CUDA(cudaMemcpyAsync(ctx->d_rowoff, h.data(), sizeof(int64_t) * (nrows + 1), cudaMemcpyHostToDevice,
                               ctx->stream));
+    SQCC_CUDA(cudaMemcpyAsync(ctx->d_rowij, hij.data(), sizeof(int64_t) * hij.size(), cudaMemcpyHostToDevice,
+                              ctx->stream));
+    SQCC_CUDA(cudaMemcpyAsync(ctx->d_ioff, ctx->h_ioff.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
     return SQCC_OK;
+}
+
+// local row range [lo, hi) of the held rows whose pair index lies in [ij_lo, ij_hi)
+static void local_row_range(const sqcc_ctx *ctx, int64_t ij_lo, int64_t ij_hi, int64_t &lo, int64_t &hi)
+{
+    auto count_before = [&](int64_t ij) {   // held rows with pair index < ij
+        if (ij <= 0) return (int64_t)0;
+        if (ij >= pair_index(ctx->n, 0)) return ctx->nrows;
+        int i, j;
+        pair_unrank(ij, i, j);
+        int64_t c = ctx->h_rowptr[i];
+        const int a = ctx->jlo[i], b = ctx->jhi[i];
+        if (j > a) c += (j < b ? j : b) - a;
+        return c;
+    };
+    lo = count_before(ij_lo);
+    hi = count_before(ij_hi);
 }
 
 // ---- synthetic generator: bit-identical to oracle/synth.py and oracle/csrc/jk_oracle.c --------------
@@ -71,14 +184,14 @@ enum { SRC_SYNTH = 0, SRC_FULL_SLAB = 1, SRC_CANONICAL = 2 };
 // One CTA per row (i,j); warps stride over sub-rows k, lanes over l (coalesced writes / reads).
 template <int SRC>
 __global__ void __launch_bounds__(256) fill_rows_kernel(double *__restrict__ P, const int64_t *__restrict__ rowoff,
-                                                        int64_t ij_begin, int64_t row_lo, int64_t row_hi, int n,
+                                                        const int64_t *__restrict__ rowij, int64_t row_lo, int64_t row_hi, int n,
                                                         uint64_t seed, const double *__restrict__ src, int p0,
                                                         int64_t canon_base)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint64_t np_ = (uint64_t)n * (uint64_t)(n + 1) / 2;
     for (int64_t row = row_lo + blockIdx.x; row < row_hi; row += gridDim.x) {
-        int64_t ij = ij_begin + row;
+        int64_t ij = rowij[row];
         int i, j;
         pair_unrank(ij, i, j);
         double *base = P + rowoff[row];
@@ -108,14 +221,14 @@ static int launch_fill(sqcc_ctx *ctx, int srckind, int64_t row_lo, int64_t row_h
     int64_t rows = row_hi - row_lo;
     int grid = (int)(rows < (int64_t)ctx->sm_count * 16 ? rows : (int64_t)ctx->sm_count * 16);
     if (srckind == SRC_SYNTH)
-        fill_rows_kernel<SRC_SYNTH><<<grid, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, ctx->ij_begin, row_lo,
+        fill_rows_kernel<SRC_SYNTH><<<grid, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, ctx->d_rowij, row_lo,
                                                                    row_hi, ctx->n, seed, src, p0, canon_base);
     else if (srckind == SRC_FULL_SLAB)
-        fill_rows_kernel<SRC_FULL_SLAB><<<grid, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, ctx->ij_begin,
+        fill_rows_kernel<SRC_FULL_SLAB><<<grid, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, ctx->d_rowij,
                                                                        row_lo, row_hi, ctx->n, seed, src, p0,
                                                                        canon_base);
     else
-        fill_rows_kernel<SRC_CANONICAL><<<grid, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, ctx->ij_begin,
+        fill_rows_kernel<SRC_CANONICAL><<<grid, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, ctx->d_rowij,
                                                                        row_lo, row_hi, ctx->n, seed, src, p0,
                                                                        canon_base);
     ctx->launches++;
@@ -125,28 +238,24 @@ static int launch_fill(sqcc_ctx *ctx, int srckind, int64_t row_lo, int64_t row_h
 
 int eri_synth(sqcc_ctx *ctx, uint64_t seed)
 {
-    return launch_fill(ctx, SRC_SYNTH, 0, ctx->ij_end - ctx->ij_begin, seed, nullptr, 0, 0);
+    return launch_fill(ctx, SRC_SYNTH, 0, ctx->nrows, seed, nullptr, 0, 0);
 }
 
 int eri_pack_full_slab(sqcc_ctx *ctx, const double *d_slab, int p0, int np)
 {
     // rows (i, *) with i in [p0, p0+np) intersected with the shard
-    int64_t row_lo = pair_index(p0, 0), row_hi = pair_index(p0 + np, 0);
-    if (row_lo < ctx->ij_begin) row_lo = ctx->ij_begin;
-    if (row_hi > ctx->ij_end) row_hi = ctx->ij_end;
+    int64_t row_lo, row_hi;
+    local_row_range(ctx, pair_index(p0, 0), pair_index(p0 + np, 0), row_lo, row_hi);
     if (row_hi <= row_lo) return SQCC_OK;
-    row_lo -= ctx->ij_begin;
-    row_hi -= ctx->ij_begin;
     return launch_fill(ctx, SRC_FULL_SLAB, row_lo, row_hi, 0, d_slab, p0, 0);
 }
 
 int eri_pack_canonical(sqcc_ctx *ctx, const double *d_rows, int64_t ij0, int64_t nrows)
 {
-    int64_t lo = ij0 > ctx->ij_begin ? ij0 : ctx->ij_begin;
-    int64_t hi = (ij0 + nrows) < ctx->ij_end ? (ij0 + nrows) : ctx->ij_end;
+    int64_t lo, hi;
+    local_row_range(ctx, ij0, ij0 + nrows, lo, hi);
     if (hi <= lo) return SQCC_OK;
-    return launch_fill(ctx, SRC_CANONICAL, lo - ctx->ij_begin, hi - ctx->ij_begin, 0, d_rows, 0,
-                       ij0 * (ij0 + 1) / 2);
+    return launch_fill(ctx, SRC_CANONICAL, lo, hi, 0, d_rows, 0, ij0 * (ij0 + 1) / 2);
 }
 
 // ---- unpack: native (unsharded) -> full [N,N,N,N], plain integral values ---------------------------
@@ -173,8 +282,7 @@ __global__ void __launch_bounds__(256) unpack_full_kernel(const double *__restri
 
 int eri_unpack_full(sqcc_ctx *ctx, double *d_full)
 {
-    SQCC_REQUIRE(ctx->d_eri && ctx->ij_begin == 0 && ctx->ij_end == pair_index(ctx->n, 0),
-                 "sqcc_eri_unpack_full needs an unsharded ERI attached");
+    SQCC_REQUIRE(ctx->d_eri && ctx->whole, "sqcc_eri_unpack_full needs an unsharded ERI attached");
     int64_t blocks = (int64_t)ctx->n * ctx->n * ctx->n;
     unpack_full_kernel<<<(unsigned)blocks, ctx->n < 256 ? ((ctx->n + 31) / 32) * 32 : 256, 0, ctx->stream>>>(
         ctx->d_eri, ctx->d_rowoff, ctx->n, d_full);

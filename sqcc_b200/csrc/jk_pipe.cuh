@@ -34,6 +34,12 @@ __device__ __forceinline__ void cp_async_wait()
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void red_add_if(bool pred, double *ptr, double v)
 {
     asm volatile(
@@ -84,6 +90,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
     const int n = p.n, ldd = p.ldd;
     const size_t nl = (size_t)n * ldd;
     uint32_t stage_w = 0, stage_r = 0;  // ring write / read positions, persist across tasks
+    unsigned long long tr_start = 0, tr_tasks = 0;
+    if (p.trace) tr_start = globaltimer_ns();
 
     for (;;) {
         unsigned t = 0;
@@ -101,16 +109,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
         const bool full_chunk = k0 >= cbase + JK_CHUNK - 1;
         if (nkk <= 0) continue;
         const int niter = task.rb_count * nkk;
+        ++tr_tasks;
 
 #pragma unroll 4
         for (int kk = 0; kk < (SLAB ? JK_KN : 0); ++kk) s_jt[kk * 32 + lane] = make_double2(0.0, 0.0);
 
         // row-block list of the task, one entry per lane (rb_count <= 32)
         int my_i0 = 0, my_j0 = 0;
+        unsigned int my_mask = 0;
         if (lane < task.rb_count) {
             const RowBlock rbk = p.rowblocks[task.rb_begin + lane];
             my_i0 = rbk.i0;
             my_j0 = rbk.j0;
+            my_mask = rbk.mask;
         }
         // D2 tile pointer of this lane (row k0, columns l0, l0+1); lanes past the matrix edge zero-fill
         const double *d2p = p.d2 + (size_t)k0 * ldd + (lane_in ? l0 : 0);
@@ -129,35 +140,30 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                 ++prod_rbi;
                 prod_i0 = __shfl_sync(0xffffffffu, my_i0, prod_rbi);
                 prod_j0 = __shfl_sync(0xffffffffu, my_j0, prod_rbi);
-                bool all_valid = (prod_i0 + NI <= n) && (prod_j0 + NJ - 1 <= prod_i0) &&
-                                 pair_index(prod_i0, prod_j0) >= p.ij_begin &&
-                                 pair_index(prod_i0 + NI - 1, prod_j0 + NJ - 1) < p.ij_end;
+                prv = __shfl_sync(0xffffffffu, my_mask, prod_rbi);
+                const bool all_valid = prv == (1u << R) - 1u;   // every row of the block is held by this shard
                 int64_t first = -1;
                 if (all_valid) {
                     // interior row-block (the common case): row(i,j) = ioff[i] + j Te(i) + Te(j), no per-row tests
-                    prv = (1u << R) - 1u;
                     int64_t tj[NJ];
 #pragma unroll
                     for (int b = 0; b < NJ; ++b) tj[b] = subrow_offset(prod_j0 + b);
 #pragma unroll
                     for (int a = 0; a < NI; ++a) {
                         const int64_t ti = subrow_offset(prod_i0 + a);
-                        const int64_t ra = (p.ioff[prod_i0 + a] - p.shard_base) + (int64_t)prod_j0 * ti;
+                        const int64_t ra = p.ioff[prod_i0 + a] + (int64_t)prod_j0 * ti;
                         if (a == 0) first = ra + tj[0];
 #pragma unroll
                         for (int b = 0; b < NJ; ++b) poff[a * NJ + b] = (unsigned int)((ra + b * ti + tj[b] - first) * 8);
                     }
                 } else {
-                    prv = 0;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const int i = prod_i0 + r / NJ, j = prod_j0 + r % NJ;
-                        const int64_t ij = pair_index(i, j);
-                        const bool ok = (i < n) && (j <= i) && ij >= p.ij_begin && ij < p.ij_end;
+                        const bool ok = (prv >> r) & 1u;
                         int64_t off = 0;
                         if (ok) {
-                            prv |= 1u << r;
-                            off = (p.ioff[i] - p.shard_base) + (int64_t)j * subrow_offset(i) + subrow_offset(j);
+                            off = p.ioff[i] + (int64_t)j * subrow_offset(i) + subrow_offset(j);
                             if (first < 0) first = off;
                         }
                         poff[r] = ok ? (unsigned int)((off - first) * 8) : 0u;
@@ -245,6 +251,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
 
         for (int rbi = 0; rbi < task.rb_count; ++rbi) {
             const int i0 = __shfl_sync(0xffffffffu, my_i0, rbi), j0 = __shfl_sync(0xffffffffu, my_j0, rbi);
+            const unsigned int rmask = __shfl_sync(0xffffffffu, my_mask, rbi);
             if (i0 != cur_i0) {
                 flushA();
                 cur_i0 = i0;
@@ -279,8 +286,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
             __syncwarp();
             if (lane < R) {
                 const int i = i0 + lane / NJ, j = j0 + lane % NJ;
-                const int64_t ij = pair_index(i, j);
-                const bool rvalid = (i < n) && (j <= i) && ij >= p.ij_begin && ij < p.ij_end;
+                const bool rvalid = (rmask >> lane) & 1u;
                 s_w[lane] = rvalid ? __ldg(p.d2 + (size_t)i * ldd + j) : 0.0;
             }
             if (WANTK && lane < JK_KN) {
@@ -470,6 +476,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
         }
     }
     if (RING) cp_async_wait<0>();
+    if (p.trace && lane == 0) {
+        unsigned long long *tr = p.trace + 3 * (size_t)(blockIdx.x * WARPS + warp);
+        tr[0] = tr_start;
+        tr[1] = globaltimer_ns();
+        tr[2] = tr_tasks;
+    }
 }
 
 }  // namespace sqcc

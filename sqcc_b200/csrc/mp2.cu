@@ -88,7 +88,7 @@ int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2,
           const double *d_C4, int n4, double *d_out)
 {
     // C blocks are column blocks of an [N,N] AO x MO matrix: element (p, a) at C[p*N + a].
-    SQCC_REQUIRE(ctx->d_eri && ctx->ij_begin == 0 && ctx->ij_end == pair_index(ctx->n, 0),
+    SQCC_REQUIRE(ctx->d_eri && ctx->whole,
                  "the AO->MO transform needs an unsharded ERI attached");
     const int64_t n = ctx->n, npair = n * (n + 1) / 2;
     const size_t s_sz = (size_t)npair * npair;

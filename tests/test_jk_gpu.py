@@ -114,7 +114,7 @@ def test_benzene_size_222(engine):
 
 @pytest.mark.parametrize("n,world", [(10, 2), (37, 3), (70, 8), (5, 8)])
 def test_sharded_partials_sum_to_full(n, world):
-    """Pair-block sharding on ONE device: every rank's engine holds its row range, builds its partial [J;K];
+    """Pair-block sharding on ONE device: every rank's engine holds its tile range, builds its partial [J;K];
     the partials must add up to the unsharded result (what the NCCL all-reduce produces on N GPUs)."""
     from sqcc_b200.backend import FockEngine
     seed = 99 + n
@@ -129,11 +129,39 @@ def test_sharded_partials_sum_to_full(n, world):
         jsum += out[0]
         ksum += out[1:]
         # each shard's partial equals the oracle's partial for the same rows
-        rows = cjk.synth_rows(n, seed, eng.plan.ij_begin, eng.plan.ij_end)
-        jp, kp = cjk.jk_packed_rows(rows, n, eng.plan.ij_begin, eng.plan.ij_end, d)
+        jp, kp = cjk.jk_packed_segments(n, seed, eng.plan.segments(), d)
         assert np.abs(out[0] - jp).max() <= TOL and np.abs(out[1:] - kp).max() <= TOL
         eng.close()
     assert np.abs(jsum - jr).max() <= TOL and np.abs(ksum - kr).max() <= TOL
+
+
+@pytest.mark.parametrize("n,world,uhf", [(10, 2, False), (37, 3, True), (70, 8, True), (62, 8, False), (5, 8, False), (222, 4, False)])
+def test_fused_peer_exchange_single_launch(n, world, uhf):
+    """The fused exchange kernel (csrc/comm.cu: flag barriers in peer memory, slice-wise reduce + broadcast, local
+    symmetrisation) with all ranks' contexts on ONE device, emulated as a single cooperative launch (blockIdx.y =
+    rank).  Every rank must end with the full J/K, bit-identical across ranks, equal to the oracle."""
+    from sqcc_b200.backend import FockGroup
+    seed = 7 + n
+    d = synth.synth_density_uhf(n, max(1, n // 3), max(1, n // 4), 5) if uhf else synth.synth_density_rhf(n, max(1, n // 3), 5)
+    if n <= 80:
+        jr, kr = cjk.jk_packed(cjk.synth_canonical(n, seed), n, d)
+    grp = FockGroup([0] * world).attach_eri_synth(n, seed)
+    for rep in range(3):   # repeated builds exercise the epoch-numbered barriers and buffer reuse
+        outs = [o.cpu().numpy() for o in grp.jk_device(d if rep != 1 else 0.5 * d)]
+        scale = 0.5 if rep == 1 else 1.0
+        for o in outs[1:]:
+            assert np.array_equal(o, outs[0])
+        if n <= 80:
+            k = outs[0][1:] if uhf else outs[0][1]
+            assert np.abs(outs[0][0] - scale * jr).max() <= TOL and np.abs(k - scale * kr).max() <= TOL
+    if n > 80:   # sampled entries by the reference loop nest
+        ent = [(0, 0), (n - 1, n - 1), (n - 1, 0), (n // 2, n // 3), (1, 0), (n - 1, n - 2), (17, 150), (150, 17)]
+        je, ke = cjk.jk_entries(cjk.SRC_SYNTH, None, n, seed, d, ent)
+        for t, (p, q) in enumerate(ent):
+            assert abs(outs[0][0][p, q] - je[t]) <= TOL and abs(outs[0][1][p, q] - ke[t]) <= TOL
+    jo = grp.jk_device(d, want_k=False)[0].cpu().numpy()
+    assert np.abs(jo[0] - outs[0][0]).max() <= TOL
+    grp.close()
 
 
 def test_anthracene_size_494(engine):

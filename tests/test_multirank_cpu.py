@@ -1,6 +1,6 @@
 """world_size-2 (gloo, CPU) coverage of the N>1 path: pair-block shard plan + the one all-reduce of [J; K].
 
-Each rank computes the partial J/K of ITS shard rows with the oracle's C port (standing in for the GPU kernel,
+Each rank computes the partial J/K of the rows of ITS tile-range shard with the oracle's C port (standing in for the GPU kernel,
 which needs a device), the product's ``reduce_partials`` sums them, and the result must equal the unsharded build.
 """
 import os
@@ -20,8 +20,7 @@ def _worker(rank, world, port, n, seed, out_dir):
     from sqcc_b200.backend import ShardPlan, reduce_partials
     plan = ShardPlan(n, world, rank)
     d = synth.synth_density_uhf(n, 5, 3, 11)
-    rows = cjk.synth_rows(n, seed, plan.ij_begin, plan.ij_end)
-    j, k = cjk.jk_packed_rows(rows, n, plan.ij_begin, plan.ij_end, d)
+    j, k = cjk.jk_packed_segments(n, seed, plan.segments(), d)
     buf = torch.from_numpy(np.concatenate([j[None], k]))
     reduce_partials(buf)
     if rank == 0:
