@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 SEED = 20261019
 NOCC = {62: 7, 222: 21, 264: 21, 494: 47}
+WARM_MIN = 25   # untimed builds before every timed loop (>= --warmup)
 
 
 def nquad(n):
@@ -56,6 +57,8 @@ def parse():
     ap.add_argument("--nbf", type=int, default=494, help="basis functions of the synthetic packed ERI")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary (N=222/264, UHF, LDA, MP2) measurements")
     ap.add_argument("--variant", type=int, default=0, help="J/K kernel: 0 TMA pipeline, 2 direct-load, 1 simple")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: fused peer-memory exchange kernel (default) or finalize + NCCL all-reduce")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     return ap.parse_args()
 
@@ -213,7 +216,7 @@ def main():
         torch.cuda.synchronize()
 
     n = args.nbf
-    eng = FockEngine(device=local, rank=rank, world=world)
+    eng = FockEngine(device=local, rank=rank, world=world, exchange=args.exchange)
     eng.attach_eri_synth(n, SEED)
     eng.set_jk_variant(args.variant)
     eng.synchronize()
@@ -223,8 +226,10 @@ def main():
     native_bytes, algo_bytes = eng.eri_bytes()
     peak, peak_src = peaks()
 
-    # ---- device-resident throughput (value)
-    for _ in range(args.warmup):
+    # ---- device-resident throughput (value).  Untimed warm-up: at least WARM_MIN builds -- the first ~20 builds after
+    # the ERI fill run 3-5 % slower (clock / power-state ramp, seen on every rank of the 8-GPU runs)
+    warm = max(args.warmup, WARM_MIN)
+    for _ in range(warm):
         eng.jk_device(d_dev, True, out)
     barrier()
     sampler = ClockSampler(local)
@@ -259,13 +264,36 @@ def main():
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
     achieved = float(ab.item()) / (float(kt.item()) * 1e-3) / 1e9  # GB/s on the slowest rank's shard
 
-    # ---- end to end through host buffers
-    for _ in range(max(1, args.warmup // 2)):
-        eng.jk(d_host)
+    # ---- the same steps with the other exchange (N > 1): finalize + NCCL all-reduce vs the fused peer-memory kernel
+    other = None
+    if world > 1:
+        alt = "nccl" if args.exchange == "p2p" else "p2p"
+        eng.set_exchange(alt)
+        for _ in range(warm):
+            eng.jk_device(d_dev, True, out)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            eng.jk_device(d_dev, True, out)
+        a1.record()
+        barrier()
+        ams = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(ams, op=dist.ReduceOp.MAX)
+        other = {"exchange": alt, "ms_per_step": float(ams.item()) / args.steps,
+                 "builds_per_s": 1e3 * args.steps / float(ams.item())}
+        eng.set_exchange(args.exchange)
+
+    # ---- end to end through host buffers: pinned host D in, pinned host J/K out, H2D + D2H inside every step
+    d_pin = eng.pinned(n, n)
+    d_pin[...] = d_host
+    jk_pin = (eng.pinned(n, n), eng.pinned(1, n, n))
+    for _ in range(warm):
+        eng.jk(d_pin, out=jk_pin)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        j_h, k_h = eng.jk(d_host)
+        j_h, k_h = eng.jk(d_pin, out=jk_pin)
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.device)
     if world > 1:
@@ -275,12 +303,15 @@ def main():
     if rank == 0:
         line = {
             "metric": "J/K Fock builds/sec", "value": 1e3 / ms_per_step, "unit": "builds/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "warmup_actual": warm, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"RHF J+K Fock build, synthetic 8-fold packed ERI, N={n} basis functions "
                                    f"(anthracene def2-TZVP size), pair-block sharded over {world} GPU(s)",
                        "nbf": n, "nquad": nquad(n), "packed_gb_algorithmic": nquad(n) * 8 / 1e9,
-                       "native_gb_rank0": native_bytes / 1e9, "parallelism": f"pair-block shard x{world} + all-reduce",
+                       "native_gb_rank0": native_bytes / 1e9,
+                       "parallelism": f"pair-block (4x4 tile) shard x{world}" + ("" if world == 1 else
+                                      (" + fused peer-memory exchange kernel (NVLink)" if args.exchange == "p2p"
+                                       else " + NCCL all-reduce")),
                        "l2_policy": "inputs larger than L2 (ERI shard >> 126 MB streamed every step)"},
             "eri_gbs_aggregate": nquad(n) * 8 / (ms_per_step * 1e-3) / 1e9,
             "frac_of_8tbs_per_gpu": nquad(n) * 8 / (ms_per_step * 1e-3) / 1e9 / world / 8000.0,
@@ -291,6 +322,8 @@ def main():
                     "d2h_bytes_per_step": int(2 * n * n * 8)},
             "gpu_launches": int(launches), "clocks": clocks, "rank_kernel_ms": rank_ms,
         }
+        if other:
+            line["exchange_alternative"] = other
         if world == 1:
             line["cpu_baseline"] = cpu_port_baseline(n, d_host, args.cpu_seconds)
         if world == 1 and not args.no_extras:
@@ -299,6 +332,7 @@ def main():
             except Exception as exc:  # extras never invalidate the headline line
                 line["extras"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
+    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

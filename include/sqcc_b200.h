@@ -95,7 +95,8 @@ int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full);
  * outputs are this rank's PARTIAL (already symmetrised) J/K -- sum over ranks gives the full matrices -- unless a
  * peer group is attached (sqcc_comm_attach below), in which case they are the full matrices on every rank. */
 int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_J, double *d_K);
-/* Same through host buffers (H2D of D, D2H of J/K inside; stream-synchronous). */
+/* Same through host buffers (H2D of D, D2H of J/K inside; stream-synchronous).  Page-locked host buffers are copied
+ * from / to directly; pageable ones go through the context's pinned staging area. */
 int sqcc_jk_build_host(sqcc_ctx *ctx, const double *h_D, int nspin, int want_k, double *h_J, double *h_K);
 /* Select the kernel: 0 = cp.async-pipelined warp-task kernel (default), 1 = simple atomics kernel (cross-check),
  * 2 = warp-task kernel with direct 128-bit global loads (no shared-memory ring), 16+c = tuning configuration c. */
@@ -122,6 +123,11 @@ int sqcc_comm_attach(sqcc_ctx *ctx, int world, int rank, const void *handles /* 
 int sqcc_comm_attach_local(sqcc_ctx **ctxs, int world);
 int sqcc_comm_detach(sqcc_ctx *ctx);
 int sqcc_comm_status(sqcc_ctx *ctx);
+/* enabled = 0: sqcc_jk_build returns this rank's partials although a group is attached (A/B against an all-reduce). */
+int sqcc_comm_set_enabled(sqcc_ctx *ctx, int enabled);
+/* Tuning aid: globaltimer (ns) at the phase boundaries of the last exchange launch on this rank: start, after barrier A,
+ * after the reduce+broadcast, grid barrier done, after barrier B, end (out8[6..7] unused). */
+int sqcc_comm_stamps(sqcc_ctx *ctx, uint64_t *out8);
 /* prep + fused kernel only: leaves the partial accumulators in the context (no J/K output). */
 int sqcc_jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k);
 int sqcc_jk_reduce_local(sqcc_ctx **ctxs, int world, int nspin, int want_k, double **d_J, double **d_K);

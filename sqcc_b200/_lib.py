@@ -42,6 +42,8 @@ SIGNATURES = {
     "sqcc_comm_attach_local": (c_int, [ctypes.POINTER(c_void_p), c_int]),
     "sqcc_comm_detach": (c_int, [c_void_p]),
     "sqcc_comm_status": (c_int, [c_void_p]),
+    "sqcc_comm_set_enabled": (c_int, [c_void_p, c_int]),
+    "sqcc_comm_stamps": (c_int, [c_void_p, c_void_p]),
     "sqcc_jk_partial": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "sqcc_jk_reduce_local": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
     "sqcc_jk_trace": (c_int, [c_void_p, c_int, c_void_p, c_int]),

@@ -213,21 +213,46 @@ class FockEngine:
             reduce_partials(out, self.group)
         return out
 
+    def set_exchange(self, exchange):
+        """Switch between the fused peer-memory exchange ("p2p") and finalize + NCCL all-reduce ("nccl") without
+        re-attaching the shard (A/B measurements)."""
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if exchange == "p2p" and not self._p2p and self._group_size() > 1:
+            if _lib.check(self.lib.sqcc_comm_status(self.ctx)) > 1:
+                _lib.check(self.lib.sqcc_comm_set_enabled(self.ctx, 1))
+                self._p2p = True
+            else:
+                self._attach_peers()
+        elif exchange == "nccl" and self._p2p:
+            _lib.check(self.lib.sqcc_comm_set_enabled(self.ctx, 0))
+            self._p2p = False
+        self.exchange = exchange
+
     def comm_check(self):
         """Raises if a peer barrier of the fused exchange timed out (reads a mapped host word; no sync)."""
         return _lib.check(self.lib.sqcc_comm_status(self.ctx))
 
-    def jk(self, d, want_k=True):
+    def pinned(self, *shape):
+        """A page-locked float64 numpy array (torch owns the allocation): buffers handed to jk() that are pinned
+        are copied from / to directly, without the library's staging copy."""
+        t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        a = t.numpy()
+        self._pinned_keep = getattr(self, "_pinned_keep", []) + [t]
+        return a
+
+    def jk(self, d, want_k=True, out=None):
         """Host in / host out, reference semantics (hf_ksdft.py:483-495, :510-535).
 
         d [N,N] -> (J, K);  d [2,N,N] -> (J(d0+d1), K[2,N,N]);  K is None when want_k is False.
+        out: optional (J [N,N], K [nspin,N,N]) float64 arrays to fill (e.g. from pinned()).
         """
         d = np.ascontiguousarray(d, dtype=np.float64)
         nspin = 1 if d.ndim == 2 else 2
         n = self.n
         if self.world == 1 or self._p2p:
-            j = np.empty((n, n))
-            k = np.empty((nspin, n, n)) if want_k else None
+            j = np.empty((n, n)) if out is None else out[0]
+            k = (np.empty((nspin, n, n)) if out is None else out[1]) if want_k else None
             self._use_stream()
             _lib.check(self.lib.sqcc_jk_build_host(
                 self.ctx, d.ctypes.data_as(ctypes.c_void_p), nspin, int(want_k),

@@ -379,6 +379,18 @@ int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, doubl
     return jk_build(ctx, d_D, nspin, want_k, d_J, d_K);
 }
 
+// true when `p` is page-locked host memory the device can copy from / to directly (cudaHostAlloc, cudaHostRegister,
+// torch pin_memory): such buffers skip the library's pinned staging copy
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int sqcc_jk_build_host(sqcc_ctx *ctx, const double *h_D, int nspin, int want_k, double *h_J, double *h_K)
 {
     SQCC_REQUIRE(ctx && h_D && h_J && (!want_k || h_K), "null ctx / buffers");
@@ -389,14 +401,21 @@ int sqcc_jk_build_host(sqcc_ctx *ctx, const double *h_D, int nspin, int want_k, 
     SQCC_TRY(ensure_io(ctx, total * sizeof(double)));
     SQCC_TRY(ensure_pin(ctx, total * sizeof(double)));
     double *dD = ctx->d_io, *dJ = dD + nspin * nn, *dK = dJ + nn;
-    memcpy(ctx->h_pin, h_D, nspin * nn * sizeof(double));
-    SQCC_CUDA(cudaMemcpyAsync(dD, ctx->h_pin, nspin * nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const bool pin_in = is_pinned_host(h_D), pin_j = is_pinned_host(h_J), pin_k = want_k && is_pinned_host(h_K);
+    const double *src = h_D;
+    if (!pin_in) {
+        memcpy(ctx->h_pin, h_D, nspin * nn * sizeof(double));
+        src = ctx->h_pin;
+    }
+    SQCC_CUDA(cudaMemcpyAsync(dD, src, nspin * nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     SQCC_TRY(jk_build(ctx, dD, nspin, want_k, dJ, dK));
-    const size_t out = (want_k ? (size_t)nspin + 1 : 1) * nn;
-    SQCC_CUDA(cudaMemcpyAsync(ctx->h_pin + nspin * nn, dJ, out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    double *stage_j = ctx->h_pin + nspin * nn, *stage_k = stage_j + nn;
+    SQCC_CUDA(cudaMemcpyAsync(pin_j ? h_J : stage_j, dJ, nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_k)
+        SQCC_CUDA(cudaMemcpyAsync(pin_k ? h_K : stage_k, dK, nspin * nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(h_J, ctx->h_pin + nspin * nn, nn * sizeof(double));
-    if (want_k) memcpy(h_K, ctx->h_pin + (nspin + 1) * nn, nspin * nn * sizeof(double));
+    if (!pin_j) memcpy(h_J, stage_j, nn * sizeof(double));
+    if (want_k && !pin_k) memcpy(h_K, stage_k, nspin * nn * sizeof(double));
     return SQCC_OK;
 }
 

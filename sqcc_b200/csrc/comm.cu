@@ -27,6 +27,7 @@ struct CommRank {   // one rank's view of the group (device copy in sqcc_ctx::co
     double *J, *K;                          // this rank's outputs
     unsigned int *gridbar;                  // this rank's grid barrier counter
     int *status;                            // mapped host word: != 0 after a barrier timeout
+    unsigned long long *stamps;             // [8] globaltimer at the phase boundaries of the last launch (CTA 0)
     int rank;
 };
 
@@ -84,6 +85,8 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
     const size_t nl = (size_t)n * ldd;
     const int nplanes = want_k ? 1 + nspin : 1;
 
+    const bool stamp = blockIdx.x == 0 && tid == 0;
+    if (stamp) cr.stamps[0] = comm_now();
     // ---- barrier A: my accumulators are complete (the J/K kernel precedes this launch on the stream)
     if (blockIdx.x == 0 && tid < world) {
         __threadfence_system();
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
     }
     if (tid < world) wait_flag(cr.flags[me] + tid, epoch, cr.status);
     __syncthreads();
+    if (stamp) cr.stamps[1] = comm_now();
 
     // ---- phase 1: reduce slice `me` of every rank's accumulators, broadcast the sums
     {
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
 
     // ---- barrier B: every CTA of this rank has stored its sums; then every rank has
     __syncthreads();
+    if (stamp) cr.stamps[2] = comm_now();
     if (tid == 0) {
         __threadfence_system();
         atomicAdd(cr.gridbar, 1u);
@@ -129,12 +134,14 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
                 }
             }
             __threadfence_system();
+            cr.stamps[3] = comm_now();
         }
         __syncthreads();
         if (tid < world) st_release_sys(cr.flags[tid] + COMM_MAXW + me, epoch);
     }
     if (tid < world) wait_flag(cr.flags[me] + COMM_MAXW + tid, epoch, cr.status);
     __syncthreads();
+    if (stamp) cr.stamps[4] = comm_now();
 
     // ---- phase 2 (local): symmetrise into the caller's J / K
     {
@@ -153,6 +160,7 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
             }
         }
     }
+    if (stamp) cr.stamps[5] = comm_now();
 }
 
 // ---------------------------------------------------------------- host side
@@ -187,6 +195,8 @@ int comm_alloc(sqcc_ctx *ctx)
     c.epoch = 0;
     if (!c.d_gridbar) {
         SQCC_CUDA(cudaMalloc(&c.d_gridbar, sizeof(unsigned int)));
+        SQCC_CUDA(cudaMalloc(&c.d_stamps, sizeof(unsigned long long) * 8));
+        SQCC_CUDA(cudaMemset(c.d_stamps, 0, sizeof(unsigned long long) * 8));
         SQCC_CUDA(cudaMalloc(&c.d_view, sizeof(CommRank) * COMM_MAXW));
         SQCC_CUDA(cudaHostAlloc(&c.h_status, sizeof(int), cudaHostAllocMapped));
         *c.h_status = 0;
@@ -203,6 +213,7 @@ void comm_free(sqcc_ctx *ctx)
     comm_close_peers(ctx);
     cudaFree(c.d_sym);
     cudaFree(c.d_gridbar);
+    cudaFree(c.d_stamps);
     cudaFree(c.d_view);
     if (c.h_status) cudaFreeHost(c.h_status);
     c = Comm();
@@ -223,6 +234,7 @@ static void fill_view(const sqcc_ctx *ctx, CommRank &v, double *J, double *K)
     v.K = K;
     v.gridbar = c.d_gridbar;
     v.status = c.d_status;
+    v.stamps = c.d_stamps;
     v.rank = c.rank;
 }
 
@@ -251,7 +263,7 @@ int jk_reduce(sqcc_ctx *ctx, int nspin, int want_k, double *d_J, double *d_K)
         c.view_J = d_J;
         c.view_K = d_K;
     }
-    const int gx = 64;
+    const int gx = ctx->sm_count < 148 ? ctx->sm_count : 148;   // one small CTA per SM: the exchange is latency-bound
     c.epoch += 1;
     c.bar_count += (unsigned int)gx;
     return launch_reduce(ctx, c.d_view, 1, gx, nspin, want_k, c.epoch, c.bar_count);
@@ -342,6 +354,21 @@ int sqcc_comm_detach(sqcc_ctx *ctx)
 {
     SQCC_REQUIRE(ctx, "null ctx");
     comm_close_peers(ctx);
+    return SQCC_OK;
+}
+
+int sqcc_comm_stamps(sqcc_ctx *ctx, uint64_t *out8)
+{
+    SQCC_REQUIRE(ctx && out8 && ctx->comm.d_stamps, "no exchange region");
+    SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+    SQCC_CUDA(cudaMemcpy(out8, ctx->comm.d_stamps, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
+    return SQCC_OK;
+}
+
+int sqcc_comm_set_enabled(sqcc_ctx *ctx, int enabled)
+{
+    SQCC_REQUIRE(ctx, "null ctx");
+    ctx->comm.enabled = enabled != 0;
     return SQCC_OK;
 }
 

@@ -91,6 +91,7 @@ struct CommRank;
 struct Comm {
     int world = 1, rank = 0;
     bool attached = false;      // peer_base[0..world) are valid
+    bool enabled = true;        // sqcc_comm_set_enabled: false -> sqcc_jk_build returns partials even with a group attached
     bool ipc = false;           // peers were opened with cudaIpcOpenMemHandle (other processes)
     bool same_device = false;   // in-process group whose contexts share one device (single-launch emulation)
     double *d_sym = nullptr;    // symmetric region [acc 3 nl][res 3 nl][flags 2 COMM_MAXW u64]
@@ -98,6 +99,7 @@ struct Comm {
     unsigned long long epoch = 0;
     unsigned int bar_count = 0;
     unsigned int *d_gridbar = nullptr;
+    unsigned long long *d_stamps = nullptr;   // [8] phase timestamps of the last exchange launch
     CommRank *d_view = nullptr;  // [COMM_MAXW]
     bool view_valid = false;     // d_view[0] holds this rank's view for outputs (view_J, view_K)
     double *view_J = nullptr, *view_K = nullptr;

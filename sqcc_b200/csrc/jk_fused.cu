@@ -327,7 +327,7 @@ int jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_
     SQCC_TRY(jk_partial(ctx, d_D, nspin, want_k));
     const int n = ctx->n, ldd = ctx->ldd;
     SQCC_TRY(timer_start(ctx, 1));
-    if (ctx->comm.attached && ctx->comm.world > 1 && !ctx->comm.same_device) {
+    if (ctx->comm.attached && ctx->comm.enabled && ctx->comm.world > 1 && !ctx->comm.same_device) {
         // ranks on distinct devices: exchange + finalize in one kernel over NVLink peer memory (comm.cu)
         SQCC_TRY(jk_reduce(ctx, nspin, want_k, d_J, d_K));
         SQCC_TRY(timer_stop(ctx, 1));
