@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsqcc_b200.so")
+LIB_PATH = os.environ.get("SQCC_LIB") or os.path.join(_HERE, "lib", "libsqcc_b200.so")   # SQCC_LIB: A/B builds (tuning)
 
 c_int, c_i64, c_u64, c_void_p = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_void_p
 c_double_p = ctypes.POINTER(ctypes.c_double)

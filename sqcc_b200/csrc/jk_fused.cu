@@ -175,8 +175,28 @@ static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int ni, int nj)
         int g = atoi(e);
         if (g >= 1 && g <= 32) group = g;
     }
-    for (int g0 = 0; g0 < nrb; g0 += group) {
-        int g1 = g0 + group < nrb ? g0 + group : nrb;
+    // Guided grouping: a task lasts ~(row-blocks in its group) x 16 sub-rows, and nearly all (k-range, chunk) tasks of a
+    // group are full-size, so with a fixed group the last, partially filled wave of tasks idles most warps for one task
+    // duration (~85 us of a 0.53 ms kernel at N = 222, ~90 us of the 1.26 ms shards at 8 GPUs).  The group therefore
+    // shrinks towards the end of the list: never more row-blocks than would leave `tail_waves` tasks per resident warp.
+    std::vector<int64_t> cells_after(nrb + 1, 0);   // (k-range, chunk) cells of row-blocks g .. nrb-1
+    for (int g = nrb - 1; g >= 0; --g) {
+        int imax = sc.h_rowblocks[g].i0 + ni - 1;
+        if (imax > n - 1) imax = n - 1;
+        int64_t t = 0;
+        for (int k0 = 0; k0 <= imax; k0 += JK_KN) t += (k0 + JK_KN - 1 < imax ? k0 + JK_KN - 1 : imax) / JK_CHUNK + 1;
+        cells_after[g] = cells_after[g + 1] + t;
+    }
+    const int64_t resident = (int64_t)ctx->sm_count * 8;
+    const double tail_waves = getenv("SQCC_JK_TAIL") ? atof(getenv("SQCC_JK_TAIL")) : 2.0;
+    for (int g0 = 0; g0 < nrb;) {
+        int gsz = group;
+        if (tail_waves > 0.0) {
+            // cells_after / gsz tasks remain if the rest is cut in groups of gsz: keep that above tail_waves x resident
+            const int64_t lim = (int64_t)((double)cells_after[g0] / (tail_waves * (double)resident));
+            if (lim < gsz) gsz = (int)(lim < 1 ? 1 : lim);
+        }
+        int g1 = g0 + gsz < nrb ? g0 + gsz : nrb;
         // largest i in this group (list is i0-descending): first entry
         int imax = sc.h_rowblocks[g0].i0 + ni - 1;
         if (imax > n - 1) imax = n - 1;
@@ -188,6 +208,7 @@ static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int ni, int nj)
             int kmax = k0 + JK_KN - 1 < imax ? k0 + JK_KN - 1 : imax;
             for (int c = 0; c * JK_CHUNK <= kmax; ++c) sc.h_tasks.push_back({k0, c, g0, cnt});
         }
+        g0 = g1;
     }
     sc.n_tasks = (int)sc.h_tasks.size();
     if (sc.d_rowblocks) cudaFree(sc.d_rowblocks);
@@ -303,10 +324,19 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
         ctx->launches++;
         SQCC_CUDA(cudaGetLastError());
     } else if (uhf_wide && p.ntasks > 0) {
-        SQCC_TRY((launch_pipe_cfg<4, 2, 2, true, 8, 2, true, true>(ctx, p)));
+        static const int uhf_stages = getenv("SQCC_UHF_STAGES") ? atoi(getenv("SQCC_UHF_STAGES")) : 2;
+        if (uhf_stages == 4)
+            SQCC_TRY((launch_pipe_cfg<4, 2, 2, true, 8, 4, true, true>(ctx, p)));
+        else if (uhf_stages == 3)
+            SQCC_TRY((launch_pipe_cfg<4, 2, 2, true, 8, 3, true, true>(ctx, p)));
+        else
+            SQCC_TRY((launch_pipe_cfg<4, 2, 2, true, 8, 2, true, true>(ctx, p)));
     } else if (wide && p.ntasks > 0) {
+        static const int rhf_mode = getenv("SQCC_RHF_MODE") ? atoi(getenv("SQCC_RHF_MODE")) : 0;
         if (!want_k)
             SQCC_TRY((launch_pipe_cfg<4, 4, 1, false, 8, 2, true, true>(ctx, p)));
+        else if (rhf_mode == 1)   // no J~ slab (flush per sub-row), three ring stages
+            SQCC_TRY((launch_pipe_cfg<4, 4, 1, true, 8, 3, false, true>(ctx, p)));
         else
             SQCC_TRY((launch_pipe_cfg<4, 4, 1, true, 8, 2, true, true>(ctx, p)));
     } else if (p.ntasks > 0) {

@@ -34,6 +34,22 @@ __device__ __forceinline__ void cp_async_wait()
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// 64-bit pointer + 32-bit offset in units of 16 bytes, in ONE instruction (IMAD.WIDE.U32 with multiplier 16) instead
+// of an add / add-with-carry pair (a multiplier of 1 is folded back into the pair by ptxas)
+__device__ __forceinline__ const char *ptr_add_u32x16(const char *base, unsigned int off16)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"(off16), "l"((unsigned long long)base));
+    return reinterpret_cast<const char *>(r);
+}
+// xor-shuffle of a double without the volatile mov.b64 pack/unpack of the CUDA header (those survive as MOVs)
+__device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, lane_mask);
+    hi = __shfl_xor_sync(0xffffffffu, hi, lane_mask);
+    return __hiloint2double(hi, lo);
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
     unsigned long long t;
@@ -131,7 +147,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
         int prod_i0 = 0, prod_j0 = 0, prod_mode = 2;      // 0: unmasked, 1: one mask (l0 <= k), 2: per-row masks
         const char *pbase = reinterpret_cast<const char *>(p.P);   // running byte pointer: first valid row, sub-row k
         const char *d2row = reinterpret_cast<const char *>(d2p);   // running byte pointer into the D2 tile
-        unsigned int poff[R];  // BYTE offsets of the rows relative to pbase (< 4 GB: rows of <= NI adjacent i)
+        unsigned int poff[R];  // offsets of the rows relative to pbase in units of 16 bytes (rows are 128-byte aligned)
         unsigned int prv = 0;  // bit r: row r of the producer's row-block is a stored row of this shard
         double2 xn[R];         // RING == false: the next sub-row's integrals, in flight during the current FMA block
         auto issue_next = [&]() {
@@ -154,7 +170,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                         const int64_t ra = p.ioff[prod_i0 + a] + (int64_t)prod_j0 * ti;
                         if (a == 0) first = ra + tj[0];
 #pragma unroll
-                        for (int b = 0; b < NJ; ++b) poff[a * NJ + b] = (unsigned int)((ra + b * ti + tj[b] - first) * 8);
+                        for (int b = 0; b < NJ; ++b) poff[a * NJ + b] = (unsigned int)((ra + b * ti + tj[b] - first) >> 1);
                     }
                 } else {
 #pragma unroll
@@ -166,7 +182,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                             off = p.ioff[i] + (int64_t)j * subrow_offset(i) + subrow_offset(j);
                             if (first < 0) first = off;
                         }
-                        poff[r] = ok ? (unsigned int)((off - first) * 8) : 0u;
+                        poff[r] = ok ? (unsigned int)((off - first) >> 1) : 0u;
                     }
                 }
                 pbase = reinterpret_cast<const char *>(p.P + (first < 0 ? 0 : first) + l0 + subrow_offset(k0 + kk_lo));
@@ -185,23 +201,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                         const int lmax = !((prv >> r) & 1u) ? -1 : (k < i ? k : (k == i ? prod_j0 + r % NJ : -1));
                         on = l0 <= lmax;
                     }
-                    xn[r] = on ? ldg_stream(reinterpret_cast<const double *>(pbase + poff[r])) : make_double2(0.0, 0.0);
+                    xn[r] = on ? ldg_stream(reinterpret_cast<const double *>(ptr_add_u32x16(pbase, poff[r]))) : make_double2(0.0, 0.0);
                 }
             } else if (prod_mode == 0) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) cp_async16(dst + r * 512u, pbase + poff[r]);
+                for (int r = 0; r < R; ++r) cp_async16(dst + r * 512u, ptr_add_u32x16(pbase, poff[r]));
                 cp_async16(dst + R * 512u, d2row);
             } else if (prod_mode == 1) {
                 const uint32_t nb = l0 <= k ? 16u : 0u;
 #pragma unroll
-                for (int r = 0; r < R; ++r) cp_async16_zfill(dst + r * 512u, pbase + poff[r], nb);
+                for (int r = 0; r < R; ++r) cp_async16_zfill(dst + r * 512u, ptr_add_u32x16(pbase, poff[r]), nb);
                 cp_async16_zfill(dst + R * 512u, d2row, lane_in ? 16u : 0u);
             } else {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int i = prod_i0 + r / NJ;
                     const int lmax = !((prv >> r) & 1u) ? -1 : (k < i ? k : (k == i ? prod_j0 + r % NJ : -1));
-                    cp_async16_zfill(dst + r * 512u, pbase + poff[r], l0 <= lmax ? 16u : 0u);
+                    cp_async16_zfill(dst + r * 512u, ptr_add_u32x16(pbase, poff[r]), l0 <= lmax ? 16u : 0u);
                 }
                 cp_async16_zfill(dst + R * 512u, d2row, lane_in ? 16u : 0u);
             }
@@ -336,8 +352,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
 #pragma unroll
                     for (int e = 0; e < 4; ++e) r4[e] = on ? rd[e] : 0.0;
                     double sum = (r4[0] + r4[1]) + (r4[2] + r4[3]);
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    sum += shfl_xor_f64(sum, 1);
+                    sum += shfl_xor_f64(sum, 2);
                     red_add_if(red_ok[h], red_dst[h] + (red_ok[h] ? k : 0), sum);
                 }
             };
@@ -411,7 +427,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
                     if (kk > kk_lo) red_finish(k - 1);   // previous sub-row's partials, written one iteration ago
                     // publish this sub-row's NV lane partials (conflict-free shared-memory transpose)
 #pragma unroll
-                    for (int q = 0; q < NV; ++q) cd[q] += __shfl_xor_sync(0xffffffffu, cd[q], 16);
+                    for (int q = 0; q < NV; ++q) cd[q] += shfl_xor_f64(cd[q], 16);
                     __syncwarp();
                     if (lane < 16) {
 #pragma unroll
@@ -440,7 +456,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
 #pragma unroll
                 for (int a = 0; a < NI; ++a)
 #pragma unroll
-                    for (int b = 0; b < NJ; ++b) accJ[a][b] += __shfl_xor_sync(0xffffffffu, accJ[a][b], 16);
+                    for (int b = 0; b < NJ; ++b) accJ[a][b] += shfl_xor_f64(accJ[a][b], 16);
 #pragma unroll
                 for (int h = 0; h < (R + 7) / 8; ++h) {   // eight row dots per pass through the scratch
                     __syncwarp();
@@ -457,8 +473,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_pipe_kernel(const JKParams p
 #pragma unroll
                         for (int e = 0; e < 4; ++e) sum += rd[e];
                     }
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    sum += shfl_xor_f64(sum, 1);
+                    sum += shfl_xor_f64(sum, 2);
                     const int i = i0 + v / NJ, j = j0 + v % NJ;
                     const bool ok = (lane & 3) == 0 && v < R && i < n && j <= i;  // rows outside the shard add 0
                     red_add_if(ok, p.jt + (ok ? (size_t)i * ldd + j : 0), sum);
