@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 
 SEED = 20261019
 NOCC = {62: 7, 222: 21, 264: 21, 494: 47}
-WARM_MIN = 25   # untimed builds before every timed loop (>= --warmup)
+WARM_MIN = 25        # untimed builds before every timed loop (>= --warmup) ...
+WARM_SECONDS = 1.0   # ... and at least this long: clocks / power state take ~1 s to settle after the ERI fill
 
 
 def nquad(n):
@@ -228,9 +229,21 @@ def main():
 
     # ---- device-resident throughput (value).  Untimed warm-up: at least WARM_MIN builds -- the first ~20 builds after
     # the ERI fill run 3-5 % slower (clock / power-state ramp, seen on every rank of the 8-GPU runs)
-    warm = max(args.warmup, WARM_MIN)
-    for _ in range(warm):
-        eng.jk_device(d_dev, True, out)
+    def warm_up(step):
+        """max(W, WARM_MIN) untimed steps, continued until WARM_SECONDS have passed (same count on every rank)."""
+        n_done, t_start = 0, time.perf_counter()
+        while True:
+            for _ in range(max(args.warmup, WARM_MIN)):
+                step()
+            n_done += max(args.warmup, WARM_MIN)
+            torch.cuda.synchronize()
+            go = torch.tensor([1.0 if time.perf_counter() - t_start < WARM_SECONDS else 0.0], device=eng.device)
+            if world > 1:
+                dist.all_reduce(go, op=dist.ReduceOp.MAX)
+            if go.item() == 0.0:
+                return n_done
+
+    warm = warm_up(lambda: eng.jk_device(d_dev, True, out))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -269,8 +282,7 @@ def main():
     if world > 1:
         alt = "nccl" if args.exchange == "p2p" else "p2p"
         eng.set_exchange(alt)
-        for _ in range(warm):
-            eng.jk_device(d_dev, True, out)
+        warm_up(lambda: eng.jk_device(d_dev, True, out))
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
@@ -288,8 +300,7 @@ def main():
     d_pin = eng.pinned(n, n)
     d_pin[...] = d_host
     jk_pin = (eng.pinned(n, n), eng.pinned(1, n, n))
-    for _ in range(warm):
-        eng.jk(d_pin, out=jk_pin)
+    warm_up(lambda: eng.jk(d_pin, out=jk_pin))
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
