@@ -11,6 +11,8 @@
 //   B_ROWS   : B(k,n) = B[k*sb_k + n]
 //   B_KOFF   : B(k,n) = B[koff[k] + n]                    (row offsets from a table, e.g. pair(p,q)*npair)
 //   B_SYMPK  : B(k,n) = B[pair(max(k,n), min(k,n))]       (symmetric matrix stored as a packed lower triangle)
+//   B_PAIRQ  : B(k,n) = B[pair(max(k,q), min(k,q)) * sb_k + n], q = batch index  (row pair(k,q) of the pair matrix:
+//              the first AO->MO quarter; same rows as a B_KOFF table, but computed instead of loaded)
 #pragma once
 #include <stdlib.h>
 
@@ -23,7 +25,7 @@ enum GemmEpilogue {
     EPI_ATOMIC = 1,      // C += acc (split-K partial sums, red.global.add.f64)
     EPI_ROWDOT = 2       // out[m] += sum_n acc[m,n] * X[m,n]   (X has the shape/strides of C)
 };
-enum GemmBMode { B_ROWS = 0, B_KOFF = 1, B_SYMPK = 2 };
+enum GemmBMode { B_ROWS = 0, B_KOFF = 1, B_SYMPK = 2, B_PAIRQ = 3 };
 
 struct GemmArgs {
     const double *A;
@@ -196,11 +198,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
 // CTA = 4 warps laid out WM x WN, every warp a (8 MT) x 32 sub-tile (MT x 4 m8n8 accumulators, MT + 4 fragment loads
 // per 4 MT DMMAs), CTA tile BM x BN x 16 with BM = 8 MT WM, BN = 32 WN.  Operands go global -> shared with 8-byte
 // cp.async (any double alignment; out-of-range elements zero-filled) through a PSTAGES-deep ring, one commit group per
-// k-tile, so PSTAGES - 1 tiles are in flight while the tensor pipe works.  <1,4,MT> (BM = 8 MT <= 32, BN = 128) serves
+// k-tile, so PSTAGES - 1 tiles are in flight while the tensor pipe works (plus the other CTAs of the SM).  <1,4,MT> (BM = 8 MT <= 32, BN = 128) serves
 // the skinny products with M = n_occ; <2,2,4> (64 x 64) the rest.
 // (Tried and dropped: several batch entries per CTA with the ring running across the batch boundaries -- the flattened
 // loop was 20-45 % slower on the M = 21, K = 222 first quarter than one CTA per product.)
-constexpr int PSTAGES = 4;
 
 __device__ __forceinline__ void cp_async8_zfill(double *smem_dst, const double *src, bool on)
 {
@@ -209,22 +210,22 @@ __device__ __forceinline__ void cp_async8_zfill(double *smem_dst, const double *
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
 }
 
-template <int WM, int WN, int MT>
+template <int WM, int WN, int MT, int PSTAGES, int BK>
 constexpr int gemm_pipe_smem_bytes()
 {
-    return PSTAGES * GEMM_BK * ((8 * MT * WM + 4) + (32 * WN + 4)) * (int)sizeof(double);
+    return PSTAGES * BK * ((8 * MT * WM + 4) + (32 * WN + 4)) * (int)sizeof(double);
 }
 
-template <bool A_MFAST, int BMODE, int WM, int WN, int MT>
+template <bool A_MFAST, int BMODE, int WM, int WN, int MT, int PSTAGES, int BK>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmArgs g)
 {
     static_assert(WM * WN == 4, "four warps");
     constexpr int BM = 8 * MT * WM, BN = 32 * WN;
     constexpr int LDA_S = BM + 4, LDB_S = BN + 4;          // == 4 (mod 8): conflict-free fragment loads
-    constexpr int EA = (BM * GEMM_BK + GEMM_THREADS - 1) / GEMM_THREADS, EB = BN * GEMM_BK / GEMM_THREADS;
+    constexpr int EA = (BM * BK + GEMM_THREADS - 1) / GEMM_THREADS, EB = BN * BK / GEMM_THREADS;
     extern __shared__ __align__(16) double gsm[];
     double *As = gsm;                                       // [PSTAGES][BK][LDA_S]
-    double *Bs = gsm + PSTAGES * GEMM_BK * LDA_S;           // [PSTAGES][BK][LDB_S]
+    double *Bs = gsm + PSTAGES * BK * LDA_S;           // [PSTAGES][BK][LDB_S]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp / WN) * (8 * MT), wn = (warp % WN) * 32;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -232,17 +233,17 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmA
     const double *A = g.A + (int64_t)bz * g.batch_a;
     const double *B = g.B + (int64_t)bz * g.batch_b;
     const int64_t *koff = BMODE == B_KOFF ? g.koff + (int64_t)bz * g.batch_koff : nullptr;
-    const int ktiles = (g.K + GEMM_BK - 1) / GEMM_BK;
+    const int ktiles = (g.K + BK - 1) / BK;
 
     auto issue_tile = [&](int kt, int stage) {
-        const int kbase = kt * GEMM_BK;
-        double *as = As + stage * GEMM_BK * LDA_S, *bs = Bs + stage * GEMM_BK * LDB_S;
+        const int kbase = kt * BK;
+        double *as = As + stage * BK * LDA_S, *bs = Bs + stage * BK * LDB_S;
 #pragma unroll
         for (int e = 0; e < EA; ++e) {
             const int idx = tid + e * GEMM_THREADS;
-            if (BM * GEMM_BK % GEMM_THREADS != 0 && idx >= BM * GEMM_BK) break;
+            if (BM * BK % GEMM_THREADS != 0 && idx >= BM * BK) break;
             int m, k;
-            if (A_MFAST) { m = idx % BM; k = idx / BM; } else { k = idx & 15; m = idx >> 4; }
+            if (A_MFAST) { m = idx % BM; k = idx / BM; } else { k = idx % BK; m = idx / BK; }
             const int gm = m0 + m, gk = kbase + k;
             const bool on = gm < g.M && gk < g.K;
             cp_async8_zfill(as + k * LDA_S + m, on ? A + (int64_t)gm * g.sa_m + (int64_t)gk * g.sa_k : A, on);
@@ -257,7 +258,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmA
             if (on) {
                 if (BMODE == B_ROWS) src = B + (int64_t)gk * g.sb_k + gn;
                 else if (BMODE == B_KOFF) src = B + __ldg(koff + gk) + gn;
-                else {
+                else if (BMODE == B_PAIRQ) {
+                    const int64_t hi = gk > bz ? gk : bz, lo = gk > bz ? bz : gk;
+                    src = g.B + (hi * (hi + 1) / 2 + lo) * g.sb_k + gn;
+                } else {
                     const int64_t hi = gk > gn ? gk : gn, lo = gk > gn ? gn : gk;
                     src = B + hi * (hi + 1) / 2 + lo;
                 }
@@ -282,9 +286,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmA
         __syncthreads();                                                          // ... everyone's; stage (kt-1)%P is free
         if (kt + PSTAGES - 1 < ktiles) issue_tile(kt + PSTAGES - 1, (kt + PSTAGES - 1) % PSTAGES);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        const double *as = As + (kt % PSTAGES) * GEMM_BK * LDA_S, *bs = Bs + (kt % PSTAGES) * GEMM_BK * LDB_S;
+        const double *as = As + (kt % PSTAGES) * BK * LDA_S, *bs = Bs + (kt % PSTAGES) * BK * LDB_S;
 #pragma unroll
-        for (int ks = 0; ks < GEMM_BK; ks += 4) {
+        for (int ks = 0; ks < BK; ks += 4) {
             double af[MT], bf[4];
 #pragma unroll
             for (int i = 0; i < MT; ++i) af[i] = as[(ks + (lane & 3)) * LDA_S + wm + i * 8 + (lane >> 2)];
@@ -313,12 +317,12 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmA
     }
 }
 
-template <bool MF, int BMD, int WM, int WN, int MT>
-inline int gemm_pipe_launch(sqcc_ctx *ctx, const GemmArgs &g)
+template <bool MF, int BMD, int WM, int WN, int MT, int PSTAGES, int BK>
+inline int gemm_pipe_launch_st(sqcc_ctx *ctx, const GemmArgs &g)
 {
     constexpr int BM = 8 * MT * WM, BN = 32 * WN;
-    constexpr int smem = gemm_pipe_smem_bytes<WM, WN, MT>();
-    auto kern = gemm_f64_pipe_kernel<MF, BMD, WM, WN, MT>;
+    constexpr int smem = gemm_pipe_smem_bytes<WM, WN, MT, PSTAGES, BK>();
+    auto kern = gemm_f64_pipe_kernel<MF, BMD, WM, WN, MT, PSTAGES, BK>;
     static bool attr_done = false;   // one attribute call per instantiation
     if (!attr_done) {
         SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -330,6 +334,23 @@ inline int gemm_pipe_launch(sqcc_ctx *ctx, const GemmArgs &g)
     ctx->launches++;
     SQCC_CUDA(cudaGetLastError());
     return SQCC_OK;
+}
+
+template <bool MF, int BMD, int WM, int WN, int MT>
+inline int gemm_pipe_launch(sqcc_ctx *ctx, const GemmArgs &g)
+{
+    // tuning knobs; default BK = 16 with a 2-deep ring: at 41 KB per CTA five CTAs share an SM, and on the short-K
+    // (K = N <= 680) quarter transforms that occupancy beats a deeper ring (N = 222: 2 stages 5.9 ms, 3: 6.3, 4: 6.9)
+    static const int st = getenv("SQCC_GEMM_STAGES") ? atoi(getenv("SQCC_GEMM_STAGES")) : 2;
+    static const int bk = getenv("SQCC_GEMM_BK") ? atoi(getenv("SQCC_GEMM_BK")) : 16;
+    if (bk == 8) {
+        if (st == 6) return gemm_pipe_launch_st<MF, BMD, WM, WN, MT, 6, 8>(ctx, g);
+        if (st == 3) return gemm_pipe_launch_st<MF, BMD, WM, WN, MT, 3, 8>(ctx, g);
+        return gemm_pipe_launch_st<MF, BMD, WM, WN, MT, 4, 8>(ctx, g);
+    }
+    if (st == 4) return gemm_pipe_launch_st<MF, BMD, WM, WN, MT, 4, 16>(ctx, g);
+    if (st == 3) return gemm_pipe_launch_st<MF, BMD, WM, WN, MT, 3, 16>(ctx, g);
+    return gemm_pipe_launch_st<MF, BMD, WM, WN, MT, 2, 16>(ctx, g);
 }
 
 template <bool MF, int BMD>
@@ -349,6 +370,7 @@ inline int gemm_f64_store(sqcc_ctx *ctx, const GemmArgs &g, int bmode)
     if (mfast) {
         if (bmode == B_ROWS) return gemm_pipe_shape<true, B_ROWS>(ctx, g);
         if (bmode == B_KOFF) return gemm_pipe_shape<true, B_KOFF>(ctx, g);
+        if (bmode == B_PAIRQ) return gemm_pipe_shape<true, B_PAIRQ>(ctx, g);
         return gemm_pipe_shape<true, B_SYMPK>(ctx, g);
     }
     SQCC_REQUIRE(bmode == B_ROWS, "packed B operands need the A^T form");

@@ -13,6 +13,7 @@
 //   Q4  [n1 n2 n3 x n4]      = T3 [n1 n2 n3 x N] . C4 [N x n4]
 // Each quarter is a (batched) DMMA GEMM (gemm_f64.cuh).
 #include <math.h>
+#include <stdlib.h>
 
 #include "gemm_f64.cuh"
 
@@ -55,16 +56,21 @@ __global__ void __launch_bounds__(256) symmetrize_pairs_kernel(const double *__r
     int k = 0, l = 0;
     if (rs < npair) pair_unrank_dev(rs, k, l);
     const int64_t coloff = subrow_offset(k) + l;
+    const double fkl = k == l ? 2.0 : 1.0;          // 1 / degeneracy factors are exact powers of two
+    // (i, j) of this warp's first row, then stepped by 8 rows at a time (no sqrt per row)
+    int i = 0, j = 0;
+    pair_unrank_dev(R0 + warp < npair ? R0 + warp : npair - 1, i, j);
     for (int r = warp; r < 32; r += 8) {
         const int64_t pq = R0 + r;
         double v = 0.0;
         if (pq < npair && rs <= pq) {
-            int i, j;
-            pair_unrank_dev(pq, i, j);
-            v = P[rowoff[pq] + coloff] / degeneracy(i, j, k, l);
+            const double f = fkl * (i == j ? 2.0 : 1.0) * (rs == pq ? 2.0 : 1.0);
+            v = P[rowoff[pq] + coloff] * f;
             S[pq * npair + rs] = v;
         }
         tile[r][lane] = v;
+        j += 8;
+        while (j > i) { j -= i + 1; ++i; }
     }
     __syncthreads();
     for (int r = warp; r < 32; r += 8) {
@@ -120,12 +126,12 @@ int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2,
     {
         GemmArgs h = g;
         h.A = d_C1; h.sa_m = 1; h.sa_k = n;
-        h.B = S; h.sb_k = 0; h.koff = koff; h.batch_koff = n;
+        h.B = S; h.sb_k = npair; h.koff = koff; h.batch_koff = n;
         h.C = T1; h.sc_m = n * npair;
         h.M = n1; h.N = (int)npair; h.K = (int)n;
         h.batch = (int)n; h.batch_a = 0; h.batch_b = 0; h.batch_c = npair;
         SQCC_REQUIRE(npair < ((int64_t)1 << 31), "npair too large");
-        SQCC_TRY(gemm_f64(ctx, h, EPI_STORE, B_KOFF));
+        SQCC_TRY(gemm_f64(ctx, h, EPI_STORE, getenv("SQCC_GEMM_OLD") ? B_KOFF : B_PAIRQ));
     }
     // Q2: T2[a, q, c, s] = sum_r C3[r, c] T1[a, q, pair(r,s)]   batch over (a, q); T1_aq read as packed symmetric
     {
