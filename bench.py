@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 SEED = 20261019
 NOCC = {62: 7, 222: 21, 264: 21, 494: 47}
 WARM_MIN = 25        # untimed builds before every timed loop (>= --warmup) ...
-WARM_SECONDS = 1.0   # ... and at least this long: clocks / power state take ~1 s to settle after the ERI fill
+WARM_SECONDS = 0.3   # ... and at least this long: clocks take ~0.1 s to ramp after the ERI fill (matters for the ms-long steps at N > 1)
 
 
 def nquad(n):
