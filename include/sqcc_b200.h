@@ -154,9 +154,24 @@ int sqcc_mp2_host(sqcc_ctx *ctx, const double *h_C, const double *h_eps, int n_o
 int sqcc_ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2, const double *d_C3, int n3,
                const double *d_C4, int n4, double *d_out);
 
+/* ---- device-resident SCF iteration ------------------------------------------------------
+ * Replaces, between two Fock builds, the host steps hf_ksdft.py:498-504 / :527-548 (Fock), :552-587 (electronic
+ * energy), :97-123 + :604-621 (X^T F X, eigh, C = X C') and :150-156 / :178-199 + :625 (density): D, J/K, V_xc, F, C
+ * stay in HBM, one double (E_elec) is read back per iteration.  eigh is cuSOLVER Dsyevd (dlopen'ed on first use).
+ *   setup        H_core [N,N], X = S^-1/2 [N,N] (host), nspin = 1 restricted / 2 unrestricted, occupations, ksdft flag
+ *   set_density  initial density [nspin,N,N] (host)
+ *   fock_energy  J/K (+ LDA V_xc) of the resident density, Fock matrices, *h_e_elec = electronic energy
+ *   update       new orbitals and density from the current Fock matrices (the reference skips this after convergence)
+ *   get          density [nspin,N,N], C^T [nspin,N,N] (row k = MO k), orbital energies [nspin,N] to the host */
+int sqcc_scf_setup(sqcc_ctx *ctx, const double *h_H, const double *h_X, int nspin, int n_occ_a, int n_occ_b, int ksdft);
+int sqcc_scf_set_density(sqcc_ctx *ctx, const double *h_D);
+int sqcc_scf_fock_energy(sqcc_ctx *ctx, double *h_e_elec);
+int sqcc_scf_update(sqcc_ctx *ctx);
+int sqcc_scf_get(sqcc_ctx *ctx, double *h_D, double *h_Ct, double *h_eps);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* CUDA-event duration (ms) of the last call's dominant kernel(s): slot 0 = J/K kernel, 1 = J/K finalize,
- * 2 = rho, 3 = vxc, 4 = mp2 transforms, 5 = mp2 energy.  Returns the number of slots written. */
+ * 2 = rho, 3 = vxc, 4 = mp2 transforms, 5 = mp2 energy, 6 = SCF update (X^T F X, eigh, density).  Returns the number of slots written. */
 int sqcc_get_timings(sqcc_ctx *ctx, double *ms, int n);
 /* Number of library kernels launched since context creation. */
 int64_t sqcc_launch_count(sqcc_ctx *ctx);

@@ -55,6 +55,11 @@ SIGNATURES = {
     "sqcc_mp2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "sqcc_mp2_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "sqcc_ao2mo": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "sqcc_scf_setup": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
+    "sqcc_scf_set_density": (c_int, [c_void_p, c_void_p]),
+    "sqcc_scf_fock_energy": (c_int, [c_void_p, c_double_p]),
+    "sqcc_scf_update": (c_int, [c_void_p]),
+    "sqcc_scf_get": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "sqcc_get_timings": (c_int, [c_void_p, c_double_p, c_int]),
     "sqcc_launch_count": (c_i64, [c_void_p]),
     "sqcc_eri_bytes": (c_int, [c_void_p, c_i64_p, c_i64_p]),

@@ -266,6 +266,38 @@ class FockEngine:
             k = k[0]
         return j, k
 
+    # ------------------------------------------------------------------ device-resident SCF iteration (csrc/scf.cu)
+    def scf_setup(self, h_core, orthogonalizer, nspin, n_occ_a, n_occ_b, ksdft):
+        h = np.ascontiguousarray(h_core, dtype=np.float64)
+        x = np.ascontiguousarray(orthogonalizer, dtype=np.float64)
+        self._use_stream()
+        _lib.check(self.lib.sqcc_scf_setup(self.ctx, h.ctypes.data_as(ctypes.c_void_p), x.ctypes.data_as(ctypes.c_void_p),
+                                           int(nspin), int(n_occ_a), int(n_occ_b), int(bool(ksdft))))
+        self._scf_nspin = int(nspin)
+
+    def scf_set_density(self, d):
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        _lib.check(self.lib.sqcc_scf_set_density(self.ctx, d.ctypes.data_as(ctypes.c_void_p)))
+
+    def scf_fock_energy(self):
+        """Fock build for the resident density; returns the electronic energy (the only per-iteration D2H)."""
+        e = ctypes.c_double()
+        self._use_stream()
+        _lib.check(self.lib.sqcc_scf_fock_energy(self.ctx, ctypes.byref(e)))
+        return e.value
+
+    def scf_update(self):
+        self._use_stream()
+        _lib.check(self.lib.sqcc_scf_update(self.ctx))
+
+    def scf_get(self):
+        """(density [nspin,N,N], C [nspin,N,N] AO x MO, eps [nspin,N]) from the device."""
+        n, ns = self.n, self._scf_nspin
+        d, ct, eps = np.empty((ns, n, n)), np.empty((ns, n, n)), np.empty((ns, n))
+        _lib.check(self.lib.sqcc_scf_get(self.ctx, d.ctypes.data_as(ctypes.c_void_p), ct.ctypes.data_as(ctypes.c_void_p),
+                                         eps.ctypes.data_as(ctypes.c_void_p)))
+        return d, np.ascontiguousarray(np.transpose(ct, (0, 2, 1))), eps
+
     # ------------------------------------------------------------------ LDA grid
     def attach_grid(self, phi, w):
         phi = np.ascontiguousarray(phi, dtype=np.float64)
@@ -339,7 +371,7 @@ class FockEngine:
     def timings(self):
         buf = (ctypes.c_double * 8)()
         _lib.check(self.lib.sqcc_get_timings(self.ctx, buf, 8))
-        names = ["jk_kernel", "jk_finalize", "rho", "vxc", "mp2_transform", "mp2_energy", "t6", "t7"]
+        names = ["jk_kernel", "jk_finalize", "rho", "vxc", "mp2_transform", "mp2_energy", "scf_update", "t7"]
         return {k: buf[i] for i, k in enumerate(names)}
 
     def launch_count(self):

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsqcc_b200.so")
-SOURCES = ["api.cu", "eri_layout.cu", "jk_fused.cu", "comm.cu", "grid_lda.cu", "mp2.cu"]
+SOURCES = ["api.cu", "eri_layout.cu", "jk_fused.cu", "comm.cu", "scf.cu", "grid_lda.cu", "mp2.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(f"--- {src}\n{out}\n")
     if failed:
         raise RuntimeError("nvcc compilation of libsqcc_b200 failed")
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"], env=env)
+    subprocess.check_call([_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"], env=env)
     return LIB
 
 

@@ -173,6 +173,7 @@ int sqcc_ctx_destroy(sqcc_ctx *ctx)
         cudaFree(sc.d_tasks);
     }
     cudaFree(ctx->d_dwork);
+    scf_free(ctx);
     comm_free(ctx);
     cudaFree(ctx->d_counter);
     cudaFree(ctx->d_trace);

@@ -106,6 +106,8 @@ struct Comm {
     int *h_status = nullptr, *d_status = nullptr;   // mapped host word
 };
 
+struct ScfState;   // scf.cu
+
 struct Timer {
     cudaEvent_t a = nullptr, b = nullptr;
     bool used = false;
@@ -166,6 +168,8 @@ struct sqcc_ctx {
     double *d_mp2out = nullptr;
     size_t mp2out_n = 0;
 
+    sqcc::ScfState *scf = nullptr;   // device-resident SCF iteration state (scf.cu)
+
     sqcc::Timer timers[8];
 };
 
@@ -201,6 +205,9 @@ int jk_reduce(sqcc_ctx *ctx, int nspin, int want_k, double *d_J, double *d_K);
 int lda_vxc(sqcc_ctx *ctx, const double *d_D, int nspin, double *d_Vxc, double *d_Exc, double *d_rho);
 int grid_quadrature(sqcc_ctx *ctx, const double *d_v, double *d_V);
 int grid_rho(sqcc_ctx *ctx, const double *d_D, double *d_rho);
+
+// scf.cu
+void scf_free(sqcc_ctx *ctx);
 
 // mp2.cu
 int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2, const double *d_C3, int n3,

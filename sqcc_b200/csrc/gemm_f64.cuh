@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmA
     constexpr int BM = 8 * MT * WM, BN = 32 * WN;
     constexpr int LDA_S = BM + 4, LDB_S = BN + 4;          // == 4 (mod 8): conflict-free fragment loads
     constexpr int EA = (BM * BK + GEMM_THREADS - 1) / GEMM_THREADS, EB = BN * BK / GEMM_THREADS;
-    extern __shared__ __align__(16) double gsm[];
-    double *As = gsm;                                       // [PSTAGES][BK][LDA_S]
-    double *Bs = gsm + PSTAGES * BK * LDA_S;           // [PSTAGES][BK][LDB_S]
+    extern __shared__ __align__(128) double gemm_sm[];
+    double *As = gemm_sm;                                      // [PSTAGES][BK][LDA_S]
+    double *Bs = gemm_sm + PSTAGES * BK * LDA_S;           // [PSTAGES][BK][LDB_S]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp / WN) * (8 * MT), wn = (warp % WN) * 32;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;

@@ -13,6 +13,7 @@ J/K/V_xc differs (<= 1e-11) and iteration counts are reproduced.  The reference'
 (num_ao > 120, hf_ksdft.py:326-329) are lifted: they only protected its Python loops.
 """
 import json
+import os
 
 import numpy as np
 
@@ -27,7 +28,7 @@ ENERGY_TOL = 1.0e-9
 class Calculator:
     def __init__(self, mol_xyz, nuclear_numbers, geom_coordinates, basis_set_name, ksdft_functional_name,
                  molecular_charge, spin_multiplicity, spin_orbital_treatment, mm_coords=None, mm_charges=None,
-                 engine=None):
+                 engine=None, device_scf=None):
         self.mol_xyz = mol_xyz
         self.nuclear_numbers = nuclear_numbers
         self.geom_coordinates = geom_coordinates
@@ -59,6 +60,9 @@ class Calculator:
         else:
             raise NotImplementedError("Only the LDA exchange functional is implemented.")
         self.engine = engine          # optional pre-built FockEngine (multi-GPU runs pass their rank's engine)
+        # device_scf: keep D / J / K / F / C on the device between Fock builds (csrc/scf.cu, cuSOLVER eigh) instead of
+        # the reference's host NumPy steps; default off (exact host path), or SQCC_DEVICE_SCF=1 in the environment
+        self.device_scf = (os.environ.get("SQCC_DEVICE_SCF", "0") == "1") if device_scf is None else bool(device_scf)
         self.scf_iterations = 0
         self.scf_converged = False
         self.scf_energy_trace = []
@@ -176,7 +180,28 @@ class Calculator:
         self.scf_converged = False
         alpha_energies = beta_energies = None
         total_energy = old_total_energy = None
-        for step in range(MAX_SCF_ITER):
+        if self.device_scf:
+            # same loop with every per-iteration matrix resident in HBM: only E_elec comes back each step
+            n_a, n_b = (int(self.num_electrons / 2),) * 2 if restricted else self._occupations()
+            engine.scf_setup(core_hamiltonian, orthogonalizer, 1 if restricted else 2, n_a, n_b, self.flag_ksdft)
+            engine.scf_set_density(density)
+            for step in range(MAX_SCF_ITER):
+                total_energy = engine.scf_fock_energy() + nuclear_repulsion
+                self.scf_energy_trace.append(float(total_energy))
+                print("SCF step %s: " % str(step + 1), total_energy, "Hartree")
+                if step > 0 and abs(old_total_energy - total_energy) < ENERGY_TOL:
+                    print("SCF converged!")
+                    self.scf_converged = True
+                    break
+                old_total_energy = total_energy
+                engine.scf_update()
+            d_dev, c_dev, eps_dev = engine.scf_get()
+            if restricted:
+                density, mo_coefficients, orbital_energies = d_dev[0], c_dev[0], eps_dev[0]
+            else:
+                density, mo_coefficients = d_dev, c_dev
+                alpha_energies, beta_energies = eps_dev[0], eps_dev[1]
+        for step in range(0 if self.device_scf else MAX_SCF_ITER):
             # --- device: V_xc / E_xc (KS) and J (/K) for the current density
             xc_energy = 0.0
             vxc = None
