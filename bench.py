@@ -409,7 +409,58 @@ def extras(eng, torch):
     nv = n - no
     fl = 2.0 * no * n ** 4 + 2.0 * no * no * n ** 3 + 2.0 * no * no * nv * n * n + 2.0 * no * no * nv * nv * n
     res["mp2_N222_nocc21"] = {"transform_ms": t, "reference_flops": fl, "tflops_reference_equivalent": fl / (t * 1e-3) / 1e12}
+    res["scf_iteration"] = scf_iteration_times(eng)
     return res
+
+
+def scf_iteration_times(eng, sizes=(62, 222, 494), iters=6):
+    """Wall time of ONE SCF iteration (BASELINE metric part 3) around the J/K build, synthetic operands (random symmetric
+    H_core, X = I, synthetic ERI: the loop does not converge, the per-iteration work is what is timed):
+      host_la   the reference's structure -- J/K through host buffers, then NumPy Fock / energy / X^T F X / eigh /
+                C = X C' / density (hf_ksdft.py:498-499, :556-557, :97-123, :616-625) -- what Calculator.scf() does;
+      device_la the device-resident iteration (csrc/scf.cu): one double crosses PCIe per iteration."""
+    from sqcc_b200.hf_ksdft import Calculator
+    out = {}
+    for n in sizes:
+        eng.attach_eri_synth(n, SEED)
+        rng = np.random.default_rng(n)
+        h = rng.standard_normal((n, n))
+        h = 0.5 * (h + h.T) - 3.0 * np.eye(n)
+        x = np.eye(n)
+        nocc = NOCC.get(n, max(1, n // 10))
+        d0 = density_rhf(n, nocc, 7)
+        # host linear algebra
+        d = d0.copy()
+        t_jk = t_la = 0.0
+        for it in range(iters + 1):
+            t0 = time.perf_counter()
+            j, k = eng.jk(d)
+            t1 = time.perf_counter()
+            fock = h + j - 0.5 * k
+            _e = 0.5 * np.sum(d * (h + fock))
+            _w, cp = Calculator.solve_one_electron_problem(x, fock)
+            c = np.matmul(x, cp)
+            d = 2.0 * np.matmul(c[:, :nocc], c[:, :nocc].T)
+            t2 = time.perf_counter()
+            if it > 0:
+                t_jk += t1 - t0
+                t_la += t2 - t1
+        # device-resident
+        eng.scf_setup(h, x, 1, nocc, nocc, False)
+        eng.scf_set_density(d0)
+        eng.scf_fock_energy()
+        eng.scf_update()
+        eng.synchronize()
+        t0 = time.perf_counter()
+        for it in range(iters):
+            eng.scf_fock_energy()
+            eng.scf_update()
+        eng.synchronize()
+        t_dev = time.perf_counter() - t0
+        out[f"n{n}"] = {"host_la_ms": 1e3 * (t_jk + t_la) / iters, "host_la_jk_ms": 1e3 * t_jk / iters,
+                        "host_la_numpy_ms": 1e3 * t_la / iters, "device_la_ms": 1e3 * t_dev / iters,
+                        "device_update_kernel_ms": eng.timings()["scf_update"]}
+    return out
 
 
 if __name__ == "__main__":
