@@ -279,8 +279,9 @@ def main():
 
     # ---- the same steps with the other exchange (N > 1): finalize + NCCL all-reduce vs the fused peer-memory kernel
     other = None
-    if world > 1:
-        alt = "nccl" if args.exchange == "p2p" else "p2p"
+    used_exchange = eng.exchange       # "nccl" if the peer mapping was refused and every rank fell back
+    if world > 1 and (used_exchange == "p2p" or args.exchange == "nccl"):
+        alt = "nccl" if used_exchange == "p2p" else "p2p"
         eng.set_exchange(alt)
         warm_up(lambda: eng.jk_device(d_dev, True, out))
         barrier()
@@ -294,7 +295,7 @@ def main():
         dist.all_reduce(ams, op=dist.ReduceOp.MAX)
         other = {"exchange": alt, "ms_per_step": float(ams.item()) / args.steps,
                  "builds_per_s": 1e3 * args.steps / float(ams.item())}
-        eng.set_exchange(args.exchange)
+        eng.set_exchange(used_exchange)
 
     # ---- end to end through host buffers: pinned host D in, pinned host J/K out, H2D + D2H inside every step
     d_pin = eng.pinned(n, n)
@@ -321,7 +322,7 @@ def main():
                        "nbf": n, "nquad": nquad(n), "packed_gb_algorithmic": nquad(n) * 8 / 1e9,
                        "native_gb_rank0": native_bytes / 1e9,
                        "parallelism": f"pair-block (4x4 tile) shard x{world}" + ("" if world == 1 else
-                                      (" + fused peer-memory exchange kernel (NVLink)" if args.exchange == "p2p"
+                                      (" + fused peer-memory exchange kernel (NVLink)" if used_exchange == "p2p"
                                        else " + NCCL all-reduce")),
                        "l2_policy": "inputs larger than L2 (ERI shard >> 126 MB streamed every step)"},
             "eri_gbs_aggregate": nquad(n) * 8 / (ms_per_step * 1e-3) / 1e9,

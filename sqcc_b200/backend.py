@@ -138,18 +138,34 @@ class FockEngine:
 
     def _attach_peers(self):
         """Exchange the CUDA IPC handles of the ranks' accumulator regions (torch.distributed is only the
-        messenger) and map them: afterwards sqcc_jk_build returns the full J/K on every rank."""
+        messenger) and map them: afterwards sqcc_jk_build returns the full J/K on every rank.  If any rank cannot
+        map its peers (no peer access / IPC disabled) ALL ranks fall back to finalize + NCCL all-reduce together."""
+        import warnings
         import torch.distributed as dist
         nb = 64  # SQCC_COMM_HANDLE_BYTES
         mine = (ctypes.c_ubyte * nb)()
-        _lib.check(self.lib.sqcc_comm_export(self.ctx, mine))
+        ok = self.lib.sqcc_comm_export(self.ctx, mine) == 0
         t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
         gathered = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(gathered, t, group=self.group)
-        blob = bytes(torch.cat(gathered).cpu().numpy().tobytes())
-        _lib.check(self.lib.sqcc_comm_attach(self.ctx, self.world, self.rank, blob))
+        err = ""
+        if ok:
+            blob = bytes(torch.cat(gathered).cpu().numpy().tobytes())
+            ok = self.lib.sqcc_comm_attach(self.ctx, self.world, self.rank, blob) == 0
+            if not ok:
+                err = self.lib.sqcc_last_error().decode()
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self._p2p = True
+            return
+        self.lib.sqcc_comm_detach(self.ctx)
         dist.barrier(group=self.group)
-        self._p2p = True
+        self._p2p = False
+        self.exchange = "nccl"
+        if self.rank == 0:
+            warnings.warn("sqcc_b200: peer-memory exchange unavailable (" + (err or "a rank failed to map its peers") +
+                          "); using finalize + NCCL all-reduce")
 
     def attach_eri_synth(self, n, seed):
         """Counter-based synthetic packed ERI, generated on the device shard by shard."""
