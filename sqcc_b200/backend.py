@@ -97,24 +97,27 @@ class FockEngine:
             s = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.sqcc_ctx_set_stream(self.ctx, ctypes.c_void_p(s)))
 
-    def _detach_peers(self):
-        """Unmap the peers' regions; nobody may free its region before every rank has unmapped it."""
+    def _detach_peers(self, collective=True):
+        """Unmap the peers' regions; nobody may free its region before every rank has unmapped it (barrier).
+        collective=False (garbage collection / interpreter exit) skips the barrier: a destructor must not block on
+        ranks that may never arrive."""
         if self._p2p:
             self._p2p = False
             self.lib.sqcc_comm_detach(self.ctx)
             import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
+            if collective and dist.is_available() and dist.is_initialized():
                 dist.barrier(group=self.group)
 
-    def close(self):
+    def close(self, collective=True):
+        """Release the context.  With a peer group attached this is a collective call (all ranks close together)."""
         if getattr(self, "ctx", None):
-            self._detach_peers()
+            self._detach_peers(collective)
             self.lib.sqcc_ctx_destroy(self.ctx)
             self.ctx = None
 
     def __del__(self):
         try:
-            self.close()
+            self.close(collective=False)
         except Exception:
             pass
 
