@@ -143,19 +143,39 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
     __syncthreads();
     if (stamp) cr.stamps[4] = comm_now();
 
-    // ---- phase 2 (local): symmetrise into the caller's J / K
+    // ---- phase 2 (local): symmetrise into the caller's J / K.  Four elements per thread with all loads issued before
+    // the first store (the L2 round trips overlap instead of chaining)
     {
         const double *res = cr.res[me];
         const size_t nn = (size_t)n * n;
-        for (size_t idx = (size_t)blockIdx.x * blockDim.x + tid; idx < nn; idx += (size_t)gridDim.x * blockDim.x) {
-            const int pr = (int)(idx / n), q = (int)(idx % n);
-            const int hi = pr >= q ? pr : q, lo = pr >= q ? q : pr;
-            const double jt = __ldcg(res + (size_t)hi * ldd + lo);
-            cr.J[idx] = pr == q ? 2.0 * jt : jt;
-            if (want_k) {
-                for (int s = 0; s < nspin; ++s) {
-                    const double *kt = res + (1 + s) * nl;
-                    cr.K[(size_t)s * nn + idx] = __ldcg(kt + (size_t)pr * ldd + q) + __ldcg(kt + (size_t)q * ldd + pr);
+        const size_t stride = (size_t)gridDim.x * blockDim.x;
+        for (size_t base = (size_t)blockIdx.x * blockDim.x + tid; base < nn; base += 4 * stride) {
+            double jv[4], ka[4], kb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const size_t idx = base + u * stride;
+                jv[u] = ka[u] = kb[u] = 0.0;
+                if (idx < nn) {
+                    const int pr = (int)(idx / n), q = (int)(idx % n);
+                    const int hi = pr >= q ? pr : q, lo = pr >= q ? q : pr;
+                    const double jt = __ldcg(res + (size_t)hi * ldd + lo);
+                    jv[u] = pr == q ? 2.0 * jt : jt;
+                    if (want_k) {
+                        ka[u] = __ldcg(res + nl + (size_t)pr * ldd + q) + __ldcg(res + nl + (size_t)q * ldd + pr);
+                        if (nspin == 2)
+                            kb[u] = __ldcg(res + 2 * nl + (size_t)pr * ldd + q) + __ldcg(res + 2 * nl + (size_t)q * ldd + pr);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const size_t idx = base + u * stride;
+                if (idx < nn) {
+                    cr.J[idx] = jv[u];
+                    if (want_k) {
+                        cr.K[idx] = ka[u];
+                        if (nspin == 2) cr.K[nn + idx] = kb[u];
+                    }
                 }
             }
         }

@@ -19,7 +19,9 @@ eng.attach_eri_synth(nbf, 20261019)
 q, _ = np.linalg.qr(np.random.default_rng(7).standard_normal((nbf, nbf)))
 d = torch.from_numpy(2.0 * q[:, :nbf // 10] @ q[:, :nbf // 10].T).to(eng.device)
 out = torch.empty((2, nbf, nbf), dtype=torch.float64, device=eng.device)
-for mode in ("p2p", "nccl", "p2p"):
+rounds = int(os.environ.get("ROUNDS", "1"))
+steps = int(os.environ.get("STEPS", "20"))
+for mode in ("p2p", "nccl", "p2p") if rounds == 1 else ("p2p", "nccl") * rounds:
     eng.set_exchange(mode)
     for _ in range(3):
         eng.jk_device(d, True, out)
@@ -27,12 +29,12 @@ for mode in ("p2p", "nccl", "p2p"):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(20):
+    for _ in range(steps):
         eng.jk_device(d, True, out)
     e1.record()
     torch.cuda.synchronize()
     tm = eng.timings()
-    msg = f"rank {rank} {mode}: step {e0.elapsed_time(e1) / 20:.4f} ms  jk_kernel {tm['jk_kernel']:.4f} finalize/exchange {tm['jk_finalize']:.4f}"
+    msg = f"rank {rank} {mode}: step {e0.elapsed_time(e1) / steps:.4f} ms  jk_kernel {tm['jk_kernel']:.4f} finalize/exchange {tm['jk_finalize']:.4f}"
     if mode == "p2p":
         st = (ctypes.c_uint64 * 8)()
         eng.lib.sqcc_comm_stamps(eng.ctx, st)
