@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 SEED = 20261019
 NOCC = {62: 7, 222: 21, 264: 21, 494: 47}
 WARM_MIN = 25        # untimed builds before every timed loop (>= --warmup) ...
-WARM_SECONDS = 0.3   # ... and at least this long: clocks take ~0.1 s to ramp after the ERI fill (matters for the ms-long steps at N > 1)
+WARM_SECONDS = 1.5   # ... and at least this long: every GPU reaches its 1000 W cap within ~0.3 s of streaming and the power
+                     # controller then oscillates for ~1 s (8-GPU steps measured 1.36-1.74 ms inside that window, 1.6 ms after)
 
 
 def nquad(n):

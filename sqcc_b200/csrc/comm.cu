@@ -67,6 +67,7 @@ __device__ __forceinline__ void wait_flag(const unsigned long long *p, unsigned 
 {
     const unsigned long long t0 = comm_now();
     while (ld_acquire_sys(p) < epoch) {
+        __nanosleep(200);   // the GPUs run at their power cap: a waiting rank should not burn it polling
         if (comm_now() - t0 > COMM_TIMEOUT_NS) {
             *status = 1;
             __threadfence_system();
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
         if (tid == 0) {
             const unsigned long long t0 = comm_now();
             while ((int)(ld_acquire_gpu(cr.gridbar) - bar_target) < 0) {
+                __nanosleep(100);
                 if (comm_now() - t0 > COMM_TIMEOUT_NS) {
                     *cr.status = 2;
                     break;
