@@ -135,6 +135,35 @@ def test_sharded_partials_sum_to_full(n, world):
     assert np.abs(jsum - jr).max() <= TOL and np.abs(ksum - kr).max() <= TOL
 
 
+@pytest.mark.parametrize("n,world", [(23, 3), (41, 5), (9, 4)])
+def test_sharded_ingest_from_host_tensors(n, world):
+    """Row A on a sharded engine: every rank packs ITS tile-range shard from the full [N,N,N,N] host tensor
+    (interface_psi4.py:177-190 output; slabs through pinned staging) and from the canonical packed vector; the shard's
+    partial J/K must equal the oracle's partial for the same rows, and the partials must add up to the full J/K."""
+    from oracle import packing as pk
+    from sqcc_b200.backend import FockEngine
+    seed = 17 + n
+    packed = cjk.synth_canonical(n, seed)
+    full = pk.unpack_canonical(packed, n)
+    d = synth.synth_density_uhf(n, max(1, n // 3), max(1, n // 4), 3)
+    jr, kr = cjk.jk_packed(packed, n, d)
+    for mode in ("full", "canonical"):
+        jsum, ksum = np.zeros((n, n)), np.zeros((2, n, n))
+        for rank in range(world):
+            eng = FockEngine(rank=rank, world=world)
+            if mode == "full":
+                eng.attach_eri_full(full)
+            else:
+                eng.attach_eri_canonical(packed, n)
+            out = eng.jk_device(__import__("torch").from_numpy(d).to(eng.device)).cpu().numpy()
+            jp, kp = cjk.jk_packed_segments(n, seed, eng.plan.segments(), d)
+            assert np.abs(out[0] - jp).max() <= TOL and np.abs(out[1:] - kp).max() <= TOL, (mode, rank)
+            jsum += out[0]
+            ksum += out[1:]
+            eng.close()
+        assert np.abs(jsum - jr).max() <= TOL and np.abs(ksum - kr).max() <= TOL
+
+
 @pytest.mark.parametrize("n,world,uhf", [(10, 2, False), (37, 3, True), (70, 8, True), (62, 8, False), (5, 8, False), (222, 4, False)])
 def test_fused_peer_exchange_single_launch(n, world, uhf):
     """The fused exchange kernel (csrc/comm.cu: flag barriers in peer memory, slice-wise reduce + broadcast, local
