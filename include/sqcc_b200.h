@@ -86,6 +86,12 @@ int sqcc_eri_pack_full_slab(sqcc_ctx *ctx, const double *d_slab, int p0, int np)
 int sqcc_eri_pack_full_host(sqcc_ctx *ctx, const double *h_eri_full);
 /* Pack canonical packed rows [ij0, ij0+nrows) (device pointer to the first element of row ij0). */
 int sqcc_eri_pack_canonical(sqcc_ctx *ctx, const double *d_rows, int64_t ij0, int64_t nrows);
+/* Direct ingestion without the N^4 host tensor: dense blocks (i0..i0+ni) x (j0..) x (k0..) x
+ * (l0..), row-major [ni][nj][nk][nl] -- e.g. one per canonical shell quartet, Psi4: MintsHelper.ao_eri_shell(M,N,P,Q).
+ * d_desc holds nine int64 per block: offset into d_values, i0, ni, j0, nj, k0, nk, l0, nl.  Every element goes to its
+ * canonical position if this shard holds its row; call sqcc_eri_clear first (pad cells must be zero). */
+int sqcc_eri_clear(sqcc_ctx *ctx);
+int sqcc_eri_pack_blocks(sqcc_ctx *ctx, const double *d_values, const int64_t *d_desc, int nblk);
 /* Expand the attached (unsharded) ERI into the full [N,N,N,N] device tensor (plain values). */
 int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full);
 

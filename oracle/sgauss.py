@@ -163,6 +163,27 @@ class SGaussInterface:
         eri = 0.5 * (eri + eri.transpose(2, 3, 0, 1))
         return np.ascontiguousarray(eri, dtype="float64")
 
+    def iter_eri_shell_quartets(self, shell_sizes=None):
+        """Canonical shell quartets (M >= N, P >= Q, MN >= PQ) as dense blocks (i0, j0, k0, l0, values), the surface
+        of sqcc_b200.interface_psi4.Psi4Interface.iter_eri_shell_quartets.  `shell_sizes` groups consecutive AOs
+        into fake shells (default: ragged 1,3,2,... pattern) so that multi-function blocks are exercised."""
+        eri = self.ao_electron_repulsion_integral()
+        n = eri.shape[0]
+        if shell_sizes is None:
+            shell_sizes, pat, t = [], [1, 3, 2, 5], 0
+            while sum(shell_sizes) < n:
+                shell_sizes.append(min(pat[t % len(pat)], n - sum(shell_sizes)))
+                t += 1
+        first = np.concatenate([[0], np.cumsum(shell_sizes)])
+        ns = len(shell_sizes)
+        for m in range(ns):
+            for nn in range(m + 1):
+                for p in range(m + 1):
+                    for q in range((p if p < m else nn) + 1):
+                        yield (int(first[m]), int(first[nn]), int(first[p]), int(first[q]),
+                               eri[first[m]:first[m + 1], first[nn]:first[nn + 1], first[p]:first[p + 1],
+                                   first[q]:first[q + 1]])
+
     def get_basis_atomic_affiliation(self):
         return self.ao_center.copy()
 

@@ -33,6 +33,8 @@ SIGNATURES = {
     "sqcc_eri_pack_full_slab": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "sqcc_eri_pack_full_host": (c_int, [c_void_p, c_void_p]),
     "sqcc_eri_pack_canonical": (c_int, [c_void_p, c_void_p, c_i64, c_i64]),
+    "sqcc_eri_clear": (c_int, [c_void_p]),
+    "sqcc_eri_pack_blocks": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "sqcc_eri_unpack_full": (c_int, [c_void_p, c_void_p]),
     "sqcc_jk_build": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sqcc_jk_build_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -203,6 +203,40 @@ class FockEngine:
                 ij = e
         return self
 
+    def attach_eri_blocks(self, n, blocks, batch_doubles=8 << 20):
+        """Direct ingestion: `blocks` yields (i0, j0, k0, l0, values[ni,nj,nk,nl]) -- e.g. one
+        dense block per canonical shell quartet -- and every integral goes straight to its place in this rank's packed
+        shard; the full [N,N,N,N] host tensor is never built.  Blocks are staged through pinned memory in batches."""
+        self._alloc_shard(n)
+        _lib.check(self.lib.sqcc_eri_clear(self.ctx))
+        stage = torch.empty(batch_doubles, dtype=torch.float64, pin_memory=True)
+        stage_np = stage.numpy()
+        dev = torch.empty(batch_doubles, dtype=torch.float64, device=self.device)
+        desc, used = [], 0
+
+        def flush():
+            nonlocal desc, used
+            if not desc:
+                return
+            dev[:used].copy_(stage[:used], non_blocking=True)
+            dd = torch.tensor(desc, dtype=torch.int64).to(self.device)
+            _lib.check(self.lib.sqcc_eri_pack_blocks(self.ctx, _ptr(dev), _ptr(dd), len(desc)))
+            torch.cuda.current_stream().synchronize()
+            desc, used = [], 0
+
+        for i0, j0, k0, l0, vals in blocks:
+            vals = np.ascontiguousarray(vals, dtype=np.float64)
+            ni, nj, nk, nl = vals.shape
+            if vals.size > batch_doubles:
+                raise ValueError("block larger than the staging batch")
+            if used + vals.size > batch_doubles:
+                flush()
+            stage_np[used:used + vals.size] = vals.ravel()
+            desc.append([used, i0, ni, j0, nj, k0, nk, l0, nl])
+            used += vals.size
+        flush()
+        return self
+
     def eri_bytes(self):
         a, b = ctypes.c_int64(), ctypes.c_int64()
         _lib.check(self.lib.sqcc_eri_bytes(self.ctx, ctypes.byref(a), ctypes.byref(b)))

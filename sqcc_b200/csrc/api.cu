@@ -168,6 +168,7 @@ int sqcc_ctx_destroy(sqcc_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_rowoff);
     cudaFree(ctx->d_ioff);
+    cudaFree(ctx->d_jlo);
     for (auto &sc : ctx->sched) {
         cudaFree(sc.d_rowblocks);
         cudaFree(sc.d_tasks);
@@ -335,6 +336,19 @@ int sqcc_eri_pack_canonical(sqcc_ctx *ctx, const double *d_rows, int64_t ij0, in
     SQCC_REQUIRE(ctx && ctx->d_eri && d_rows, "no ERI attached / null rows");
     SQCC_REQUIRE(ij0 >= 0 && nrows > 0 && ij0 + nrows <= sqcc_npair(ctx->n), "row range out of bounds");
     return eri_pack_canonical(ctx, d_rows, ij0, nrows);
+}
+
+int sqcc_eri_clear(sqcc_ctx *ctx)
+{
+    SQCC_REQUIRE(ctx && ctx->d_eri, "no ERI attached");
+    SQCC_CUDA(cudaMemsetAsync(ctx->d_eri, 0, sizeof(double) * ctx->native_len, ctx->stream));
+    return SQCC_OK;
+}
+
+int sqcc_eri_pack_blocks(sqcc_ctx *ctx, const double *d_values, const int64_t *d_desc, int nblk)
+{
+    SQCC_REQUIRE(ctx && ctx->d_eri && d_values && d_desc && nblk >= 0, "no ERI attached / null block buffers");
+    return eri_pack_blocks(ctx, d_values, d_desc, nblk);
 }
 
 int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full)

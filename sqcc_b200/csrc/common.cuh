@@ -138,6 +138,7 @@ struct sqcc_ctx {
     int64_t *d_rowoff = nullptr;  // [nrows + 1] offsets of the held rows relative to the shard start
     int64_t *d_rowij = nullptr;   // [nrows] global pair index of the held rows
     int64_t *d_ioff = nullptr;    // [n] device copy of h_ioff
+    int *d_jlo = nullptr, *d_jhi = nullptr;   // [n] device copies of jlo / jhi (one allocation)
     sqcc::JKSchedule sched[3];    // row-block shapes [0]: 4x2 (RHF, J-only)  [1]: 2x2 (UHF)  [2]: 4x4 (tuning)
     int jk_variant = 0;
     int jk_cfg = 0;  // tuning knob of the pipelined kernel (warps, stages), see launch_pipe
@@ -190,6 +191,7 @@ int eri_synth(sqcc_ctx *ctx, uint64_t seed);
 int eri_pack_full_slab(sqcc_ctx *ctx, const double *d_slab, int p0, int np);
 int eri_pack_canonical(sqcc_ctx *ctx, const double *d_rows, int64_t ij0, int64_t nrows);
 int eri_unpack_full(sqcc_ctx *ctx, double *d_full);
+int eri_pack_blocks(sqcc_ctx *ctx, const double *d_values, const int64_t *d_desc, int nblk);
 
 // jk_fused.cu
 int jk_build_schedule(sqcc_ctx *ctx);

@@ -130,7 +130,13 @@ int eri_build_tables(sqcc_ctx *ctx)
     if (ctx->d_rowoff) cudaFree(ctx->d_rowoff);
     if (ctx->d_rowij) cudaFree(ctx->d_rowij);
     if (ctx->d_ioff) cudaFree(ctx->d_ioff);
+    if (ctx->d_jlo) cudaFree(ctx->d_jlo);
     ctx->d_rowoff = ctx->d_rowij = ctx->d_ioff = nullptr;
+    ctx->d_jlo = ctx->d_jhi = nullptr;
+    SQCC_CUDA(cudaMalloc(&ctx->d_jlo, sizeof(int) * 2 * n));
+    ctx->d_jhi = ctx->d_jlo + n;
+    SQCC_CUDA(cudaMemcpyAsync(ctx->d_jlo, ctx->jlo.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    SQCC_CUDA(cudaMemcpyAsync(ctx->d_jhi, ctx->jhi.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
     SQCC_CUDA(cudaMalloc(&ctx->d_rowoff, sizeof(int64_t) * (nrows + 1)));
     SQCC_CUDA(cudaMalloc(&ctx->d_rowij, sizeof(int64_t) * hij.size()));
     SQCC_CUDA(cudaMalloc(&ctx->d_ioff, sizeof(int64_t) * n));
@@ -256,6 +262,56 @@ int eri_pack_canonical(sqcc_ctx *ctx, const double *d_rows, int64_t ij0, int64_t
     local_row_range(ctx, ij0, ij0 + nrows, lo, hi);
     if (hi <= lo) return SQCC_OK;
     return launch_fill(ctx, SRC_CANONICAL, lo, hi, 0, d_rows, 0, ij0 * (ij0 + 1) / 2);
+}
+
+// ---- block ingestion: dense (i-range x j-range x k-range x l-range) blocks, e.g. shell quartets -------------------
+// the integral provider hands over one dense block per (canonical) shell quartet -- Psi4:
+// MintsHelper.ao_eri_shell(M, N, P, Q) -- and the full [N,N,N,N] host tensor of interface_psi4.py:177-190 (19 GB at
+// N = 222, 476 GB at N = 494) never exists.  Every element is moved to its canonical position (i >= j, k >= l,
+// ij >= kl) of the native layout if this shard holds row (i, j); symmetric images inside a block carry the same
+// integral, so the duplicate stores are benign.
+struct EriBlockDesc {
+    int64_t offset;              // first element of the block in the value buffer
+    int64_t i0, ni, j0, nj, k0, nk, l0, nl;
+};
+
+__global__ void __launch_bounds__(256) pack_blocks_kernel(double *__restrict__ P, const int64_t *__restrict__ ioff,
+                                                          const int *__restrict__ jlo, const int *__restrict__ jhi,
+                                                          const double *__restrict__ vals,
+                                                          const EriBlockDesc *__restrict__ desc, int nblk, int n)
+{
+    for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
+        const EriBlockDesc d = desc[b];
+        const int64_t total = d.ni * d.nj * d.nk * d.nl;
+        for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+            int l = (int)(d.l0 + e % d.nl);
+            int k = (int)(d.k0 + (e / d.nl) % d.nk);
+            int j = (int)(d.j0 + (e / (d.nl * d.nk)) % d.nj);
+            int i = (int)(d.i0 + e / (d.nl * d.nk * d.nj));
+            if (i >= n || j >= n || k >= n || l >= n) continue;
+            if (i < j) { const int t = i; i = j; j = t; }
+            if (k < l) { const int t = k; k = l; l = t; }
+            if (pair_index(i, j) < pair_index(k, l)) {
+                int t = i; i = k; k = t;
+                t = j; j = l; l = t;
+            }
+            if (j < jlo[i] || j >= jhi[i]) continue;   // row (i, j) belongs to another rank's shard
+            const int64_t off = ioff[i] + (int64_t)j * subrow_offset(i) + subrow_offset(j) + subrow_offset(k) + l;
+            P[off] = vals[d.offset + e] * degeneracy(i, j, k, l);
+        }
+    }
+}
+
+int eri_pack_blocks(sqcc_ctx *ctx, const double *d_values, const int64_t *d_desc, int nblk)
+{
+    if (nblk <= 0) return SQCC_OK;
+    static_assert(sizeof(EriBlockDesc) == 9 * sizeof(int64_t), "descriptor is nine int64");
+    const int grid = nblk < ctx->sm_count * 8 ? nblk : ctx->sm_count * 8;
+    pack_blocks_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_ioff, ctx->d_jlo, ctx->d_jhi, d_values,
+                                                     reinterpret_cast<const EriBlockDesc *>(d_desc), nblk, ctx->n);
+    ctx->launches++;
+    SQCC_CUDA(cudaGetLastError());
+    return SQCC_OK;
 }
 
 // ---- unpack: native (unsharded) -> full [N,N,N,N], plain integral values ---------------------------

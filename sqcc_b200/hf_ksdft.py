@@ -28,7 +28,7 @@ ENERGY_TOL = 1.0e-9
 class Calculator:
     def __init__(self, mol_xyz, nuclear_numbers, geom_coordinates, basis_set_name, ksdft_functional_name,
                  molecular_charge, spin_multiplicity, spin_orbital_treatment, mm_coords=None, mm_charges=None,
-                 engine=None, device_scf=None):
+                 engine=None, device_scf=None, direct_ingest=None):
         self.mol_xyz = mol_xyz
         self.nuclear_numbers = nuclear_numbers
         self.geom_coordinates = geom_coordinates
@@ -63,9 +63,26 @@ class Calculator:
         # device_scf: keep D / J / K / F / C on the device between Fock builds (csrc/scf.cu, cuSOLVER eigh) instead of
         # the reference's host NumPy steps; default off (exact host path), or SQCC_DEVICE_SCF=1 in the environment
         self.device_scf = (os.environ.get("SQCC_DEVICE_SCF", "0") == "1") if device_scf is None else bool(device_scf)
+        # direct_ingest: take the ERIs shell quartet by shell quartet (provider.iter_eri_shell_quartets) straight into
+        # the packed device shard instead of through the full [N,N,N,N] host tensor; default off, or SQCC_DIRECT_INGEST=1
+        self.direct_ingest = ((os.environ.get("SQCC_DIRECT_INGEST", "0") == "1") if direct_ingest is None
+                              else bool(direct_ingest))
+        self._eri_host = None
         self.scf_iterations = 0
         self.scf_converged = False
         self.scf_energy_trace = []
+
+    @property
+    def ao_electron_repulsion_integral(self):
+        """Full [N,N,N,N] tensor (result attribute of hf_ksdft.py:650-667).  With direct ingestion it only exists
+        packed on the device and is expanded on first access."""
+        if self._eri_host is None and self.engine is not None and self.engine.world == 1 and self.engine.n:
+            self._eri_host = self.engine.eri_full()
+        return self._eri_host
+
+    @ao_electron_repulsion_integral.setter
+    def ao_electron_repulsion_integral(self, value):
+        self._eri_host = value
 
     # ------------------------------------------------------------------ host steps (unchanged maths)
     @staticmethod
@@ -131,14 +148,18 @@ class Calculator:
         self.psi4_interface = proc
         kinetic = proc.ao_kinetic_integral()
         nuclear = proc.ao_nuclear_attraction_integral()
-        eri = proc.ao_electron_repulsion_integral()
         overlap = proc.ao_overlap_integral()
         num_ao = len(overlap)
 
         # the packed ERI tensor goes to HBM once, before the loop (replaces the host-resident N^4 operand)
         engine = self.engine if self.engine is not None else FockEngine()
         self.engine = engine
-        engine.attach_eri_full(eri)
+        if self.direct_ingest and hasattr(proc, "iter_eri_shell_quartets"):
+            eri = None       # never built on the host; ao_electron_repulsion_integral expands the device copy on demand
+            engine.attach_eri_blocks(num_ao, proc.iter_eri_shell_quartets())
+        else:
+            eri = proc.ao_electron_repulsion_integral()
+            engine.attach_eri_full(eri)
 
         grids = weights = None
         if self.flag_ksdft or self.flag_qmmm:

@@ -54,6 +54,22 @@ class Psi4Interface:
     def ao_electron_repulsion_integral(self):
         return self._as_array(self.mints.ao_eri())
 
+    def iter_eri_shell_quartets(self):
+        """Canonical shell quartets (M >= N, P >= Q, MN >= PQ) as dense blocks (i0, j0, k0, l0, values[nM,nN,nP,nQ])
+        from MintsHelper.ao_eri_shell: feeds FockEngine.attach_eri_blocks, so the full [N,N,N,N] tensor of
+        ao_electron_repulsion_integral() (interface_psi4.py:177-190) is never materialised.
+        Not exercised in this repository's tests (no Psi4 in the image); the provider-independent part is."""
+        bs = self.psi4_basis_set
+        ns = bs.nshell()
+        first = [bs.shell(s).function_index for s in range(ns)]
+        size = [bs.shell(s).nfunction for s in range(ns)]
+        for m in range(ns):
+            for n in range(m + 1):
+                for p in range(m + 1):
+                    for q in range((p if p < m else n) + 1):
+                        block = np.asarray(self.mints.ao_eri_shell(m, n, p, q), dtype="float64")
+                        yield first[m], first[n], first[p], first[q], block.reshape(size[m], size[n], size[p], size[q])
+
     def ao_overlap_integral(self):
         return self._as_array(self.mints.ao_overlap())
 

@@ -135,6 +135,38 @@ def test_sharded_partials_sum_to_full(n, world):
     assert np.abs(jsum - jr).max() <= TOL and np.abs(ksum - kr).max() <= TOL
 
 
+@pytest.mark.parametrize("n,world", [(13, 1), (30, 1), (23, 3)])
+def test_direct_block_ingest_equals_full_tensor_pack(n, world):
+    """SURVEY.md 8f rank 4: dense blocks per canonical (ragged, fake) shell quartet go straight into the packed shard;
+    the resulting native buffer must be bit-identical to the one packed from the full [N,N,N,N] tensor."""
+    from oracle import packing as pk
+    from sqcc_b200.backend import FockEngine
+    full = pk.unpack_canonical(cjk.synth_canonical(n, 5 + n), n)
+    sizes, pat, t = [], [1, 3, 2, 5], 0
+    while sum(sizes) < n:
+        sizes.append(min(pat[t % 4], n - sum(sizes)))
+        t += 1
+    first = np.concatenate([[0], np.cumsum(sizes)]).astype(int)
+
+    def blocks():
+        ns = len(sizes)
+        for m in range(ns):
+            for nn in range(m + 1):
+                for p in range(m + 1):
+                    for q in range((p if p < m else nn) + 1):
+                        yield (first[m], first[nn], first[p], first[q],
+                               full[first[m]:first[m + 1], first[nn]:first[nn + 1], first[p]:first[p + 1], first[q]:first[q + 1]])
+
+    for rank in range(world):
+        a, b = FockEngine(rank=rank, world=world), FockEngine(rank=rank, world=world)
+        a.attach_eri_full(full)
+        b.attach_eri_blocks(n, blocks(), batch_doubles=4096)     # small batches: several flushes
+        assert a.eri.numel() == b.eri.numel()
+        assert np.array_equal(a.eri.cpu().numpy(), b.eri.cpu().numpy())
+        a.close()
+        b.close()
+
+
 @pytest.mark.parametrize("n,world", [(23, 3), (41, 5), (9, 4)])
 def test_sharded_ingest_from_host_tensors(n, world):
     """Row A on a sharded engine: every rank packs ITS tile-range shard from the full [N,N,N,N] host tensor

@@ -79,6 +79,26 @@ def test_device_resident_scf_matches_reference(engine, name):
         assert abs(e - g["mp2_energy"]) <= 1e-9
 
 
+def test_scf_with_direct_ingest(engine):
+    """Same SCF through shell-quartet block ingestion (no host N^4 tensor) and the device-resident iteration."""
+    from sqcc_b200 import hf_ksdft, mp2
+    g = GOLDEN["h6_rhf"]
+    hf_ksdft.ipsi4 = sgauss.stub_module()
+    calc = hf_ksdft.Calculator(g["mol_xyz"], np.array(g["zs"]), np.array(g["coords"]), g["basis"], g["functional"],
+                               g["charge"], g["multiplicity"], g["treatment"], engine=engine, device_scf=True,
+                               direct_ingest=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        calc.scf()
+    assert calc.scf_iterations == g["iterations"]
+    assert np.abs(np.array(calc.scf_energy_trace) - np.array(g["energies"])).max() <= 1e-9
+    assert calc._eri_host is None                              # nothing was materialised on the host ...
+    eri = calc.ao_electron_repulsion_integral                  # ... until a consumer asks for it
+    assert eri.shape == (g["num_ao"],) * 4 and np.abs(eri - eri.transpose(2, 3, 0, 1)).max() <= 1e-15
+    if "mp2_energy" in g:
+        with contextlib.redirect_stdout(io.StringIO()):
+            assert abs(mp2.Calculator(calc).mp2() - g["mp2_energy"]) <= 1e-9
+
+
 def test_uhf_singlet_equals_rhf(engine):
     """tests/hf/n2_singlet vs tests/hf/n2_singlet/unrestricted pairing: same energies and iteration count."""
     a, _, _ = _run("h6_rhf", engine)
