@@ -91,6 +91,7 @@ grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w
                 }
             }
             // rho = rowdot(T, phi): lane holds T[row = lane/4 (+8)][col = 8j + 2(lane%4) + {0,1}]
+            double rsum[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int row = 8 * i + (lane >> 2);
@@ -102,12 +103,21 @@ grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w
                 }
                 part += __shfl_xor_sync(0xffffffffu, part, 1);
                 part += __shfl_xor_sync(0xffffffffu, part, 2);
-                const int64_t g = t * GF_TM + warp * 16 + row;
-                if ((lane & 3) == 0 && g < G) {
+                rsum[i] = part;
+            }
+            // point functions: every lane of a quad holds both row sums; lane%4 == 0 finishes row lane/4, lane%4 == 1
+            // row 8 + lane/4 (16 lanes busy with ONE pow each instead of 8 lanes with two pows twice).
+            // rho^(4/3) = rho * rho^(1/3): same NaN / zero behaviour as NumPy's pow, ~1 ulp from pow(rho, 4/3).
+            {
+                const int i = lane & 3;
+                const int64_t g = t * GF_TM + warp * 16 + 8 * i + (lane >> 2);
+                if (i < 2 && g < G) {
+                    const double r = i == 0 ? rsum[0] : rsum[1];
                     const double wg = w[g];
-                    if (rho_out) rho_out[s * G + g] = part;
-                    wv[s * G + g] = wg * (c_pot * pow(part, 1.0 / 3.0));   // pow like NumPy: NaN for rho < 0
-                    exc_part += wg * pow(part, 4.0 / 3.0);
+                    const double cb = pow(r, 1.0 / 3.0);   // pow like NumPy: NaN for rho < 0
+                    if (rho_out) rho_out[s * G + g] = r;
+                    wv[s * G + g] = wg * (c_pot * cb);
+                    exc_part += wg * (r * cb);
                 }
             }
         }
