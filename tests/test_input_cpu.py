@@ -31,6 +31,20 @@ def test_authored_n2_sto3g_config():
     assert mol_xyz.count("\n") == 2
 
 
+def test_authored_baseline_configs():
+    """Inputs for the other BASELINE.json configs the reference ships no sqc.conf for: O2 triplet
+    UHF and UKS-LDA def2-TZVP, benzene RHF+MP2 def2-TZVP.  They need Psi4 to run; here they must parse like any
+    reference input (unrestricted default for multiplicity 3, 16 / 42 electrons)."""
+    for name, func in (("o2_triplet_uhf_def2tzvp", "None"), ("o2_triplet_uks_lda_def2tzvp", "lda")):
+        p = _in_dir(os.path.join(HERE, "data", name), conf.get_calc_params)
+        assert list(p[1]) == [8, 8] and p[3] == "def2-tzvp" and p[4] == func
+        assert (p[5], p[6], p[7]) == (0, 3, "unrestricted") and not p[8] and not p[9]
+    p = _in_dir(os.path.join(HERE, "data", "benzene_rhf_mp2_def2tzvp"), conf.get_calc_params)
+    assert list(p[1]) == [6] * 6 + [1] * 6 and p[2].shape == (12, 3) and p[7] == "restricted" and p[9] is True
+    cc = np.linalg.norm(p[2][0] - p[2][1])
+    assert abs(cc - 1.397) < 1e-3
+
+
 def test_error_behaviour(tmp_path):
     with pytest.raises(FileNotFoundError):
         _in_dir(str(tmp_path), conf.get_calc_params)
