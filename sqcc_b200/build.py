@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsqcc_b200.so")
-SOURCES = ["api.cu", "eri_layout.cu", "jk_fused.cu", "comm.cu", "scf.cu", "grid_lda.cu", "mp2.cu"]
+SOURCES = ["api.cu", "eri_layout.cu", "jk_fused.cu", "comm.cu", "scf.cu", "gemm_f64.cu", "grid_lda.cu", "mp2.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

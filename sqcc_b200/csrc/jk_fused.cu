@@ -324,19 +324,10 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
         ctx->launches++;
         SQCC_CUDA(cudaGetLastError());
     } else if (uhf_wide && p.ntasks > 0) {
-        static const int uhf_stages = getenv("SQCC_UHF_STAGES") ? atoi(getenv("SQCC_UHF_STAGES")) : 2;
-        if (uhf_stages == 4)
-            SQCC_TRY((launch_pipe_cfg<4, 2, 2, true, 8, 4, true, true>(ctx, p)));
-        else if (uhf_stages == 3)
-            SQCC_TRY((launch_pipe_cfg<4, 2, 2, true, 8, 3, true, true>(ctx, p)));
-        else
-            SQCC_TRY((launch_pipe_cfg<4, 2, 2, true, 8, 2, true, true>(ctx, p)));
+        SQCC_TRY((launch_pipe_cfg<4, 2, 2, true, 8, 2, true, true>(ctx, p)));   // a deeper ring changes nothing (profiles/)
     } else if (wide && p.ntasks > 0) {
-        static const int rhf_mode = getenv("SQCC_RHF_MODE") ? atoi(getenv("SQCC_RHF_MODE")) : 0;
         if (!want_k)
             SQCC_TRY((launch_pipe_cfg<4, 4, 1, false, 8, 2, true, true>(ctx, p)));
-        else if (rhf_mode == 1)   // no J~ slab (flush per sub-row), three ring stages
-            SQCC_TRY((launch_pipe_cfg<4, 4, 1, true, 8, 3, false, true>(ctx, p)));
         else
             SQCC_TRY((launch_pipe_cfg<4, 4, 1, true, 8, 2, true, true>(ctx, p)));
     } else if (p.ntasks > 0) {

@@ -6,7 +6,7 @@
 // The reference repeats the identical transform a second time for (ib|ja) (mp2.py:185-228); the result is the same
 // array, so it is read transposed instead.  The full N^4 tensor is never materialised:
 //   S   [npair x npair]      the packed lower triangle of the pair matrix, symmetrised by a tiled transpose
-//   Q1  per q: [n1 x npair]  = C1^T [n1 x N] . S[pair(p,q), :]      (B rows addressed through an offset table;
+//   Q1  per q: [n1 x npair]  = C1^T [n1 x N] . S[pair(p,q), :]      (B rows addressed by computed pair index;
 //                              only canonical pairs rs are transformed: half the flops of the reference's step 1)
 //   Q2  per (a,q): [n3 x N]  = C3^T [n3 x N] . T1_aq (symmetric in (r,s), read from its packed lower triangle)
 //   Q3  per a:  [n2 x n3 N]  = C2^T [n2 x N] . T2_a [N x n3 N]
@@ -81,15 +81,6 @@ __global__ void __launch_bounds__(256) symmetrize_pairs_kernel(const double *__r
     (void)ntile;
 }
 
-__global__ void koff_kernel(int n, int64_t npair, int64_t *__restrict__ koff)
-{
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * n) return;
-    const int q = idx / n, p = idx % n;
-    const int hi = p > q ? p : q, lo = p > q ? q : p;
-    koff[idx] = ((int64_t)hi * (hi + 1) / 2 + lo) * npair;   // row pair(p,q) of S
-}
-
 int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2, const double *d_C3, int n3,
           const double *d_C4, int n4, double *d_out)
 {
@@ -100,18 +91,15 @@ int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2,
     const size_t s_sz = (size_t)npair * npair;
     const size_t t1 = (size_t)n1 * n * npair, t2 = (size_t)n1 * n * n3 * n, t3 = (size_t)n1 * n2 * n3 * n;
     const size_t t13 = t1 > t3 ? t1 : t3;   // T3 reuses T1's space (T1 is dead after Q2)
-    const size_t koff_sz = (size_t)n * n;   // int64 entries, stored in the double workspace
-    SQCC_TRY(ensure_mp2work(ctx, sizeof(double) * (s_sz + t13 + t2 + koff_sz)));
+    SQCC_TRY(ensure_mp2work(ctx, sizeof(double) * (s_sz + t13 + t2)));
     double *S = ctx->d_mp2work, *T1 = S + s_sz, *T2 = T1 + t13, *T3 = T1;
-    int64_t *koff = reinterpret_cast<int64_t *>(T2 + t2);
 
-    {   // symmetrised pair matrix + row-offset table
+    {   // symmetrised pair matrix
         const int64_t ntile = (npair + 31) / 32;
         const int64_t nblk = ntile * (ntile + 1) / 2;
         SQCC_REQUIRE(nblk < ((int64_t)1 << 31), "pair matrix too large for one launch");
         symmetrize_pairs_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, npair, ntile, S);
-        koff_kernel<<<(unsigned)((n * n + 255) / 256), 256, 0, ctx->stream>>>((int)n, npair, koff);
-        ctx->launches += 2;
+        ctx->launches += 1;
         SQCC_CUDA(cudaGetLastError());
     }
 
@@ -126,12 +114,12 @@ int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2,
     {
         GemmArgs h = g;
         h.A = d_C1; h.sa_m = 1; h.sa_k = n;
-        h.B = S; h.sb_k = npair; h.koff = koff; h.batch_koff = n;
+        h.B = S; h.sb_k = npair;
         h.C = T1; h.sc_m = n * npair;
         h.M = n1; h.N = (int)npair; h.K = (int)n;
         h.batch = (int)n; h.batch_a = 0; h.batch_b = 0; h.batch_c = npair;
         SQCC_REQUIRE(npair < ((int64_t)1 << 31), "npair too large");
-        SQCC_TRY(gemm_f64(ctx, h, EPI_STORE, getenv("SQCC_GEMM_OLD") ? B_KOFF : B_PAIRQ));
+        SQCC_TRY(gemm_f64(ctx, h, EPI_STORE, B_PAIRQ));
     }
     // Q2: T2[a, q, c, s] = sum_r C3[r, c] T1[a, q, pair(r,s)]   batch over (a, q); T1_aq read as packed symmetric
     {
