@@ -60,7 +60,7 @@ static int load_cusolver()
 struct ScfState {
     int n = 0, nspin = 1, nocc[2] = {0, 0}, ksdft = 0;
     double *buf = nullptr;   // one allocation, carved below
-    double *H, *X, *D, *JK, *VXC, *F, *T, *FP, *CT, *W, *E;   // E: [0] electronic energy, [1] E_xc
+    double *H, *X, *D, *JK, *VXC, *F, *T, *FP, *CT, *W, *E, *EP;   // E: [0] electronic energy, [1] E_xc; EP: block partials
     double *work = nullptr;
     int lwork = 0;
     int *info = nullptr;
@@ -124,7 +124,18 @@ __global__ void __launch_bounds__(256) scf_fock_energy_kernel(const double *__re
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-        atomicAdd(E, s);
+        E[blockIdx.x] = s;   // block partial; summed in a fixed order below
+    }
+}
+
+// Fixed-order sum of the block partials: every rank of a multi-GPU run must get the bit-identical energy (the ranks take
+// the |dE| < 1e-9 decision independently and have to agree on it).
+__global__ void scf_energy_sum_kernel(const double *__restrict__ part, int nparts, double *__restrict__ E)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int b = 0; b < nparts; ++b) s += part[b];
+        E[0] = s;
     }
 }
 
@@ -177,7 +188,7 @@ int sqcc_scf_setup(sqcc_ctx *ctx, const double *h_H, const double *h_X, int nspi
     s->ksdft = ksdft;
     const size_t nn = (size_t)n * n;
     // H, X, D[2], JK[3], VXC[2], F[2], T, FP, CT[2], W[2 n], E[2]
-    const size_t total = nn * (1 + 1 + 2 + 3 + 2 + 2 + 1 + 1 + 2) + 2 * (size_t)n + 2;
+    const size_t total = nn * (1 + 1 + 2 + 3 + 2 + 2 + 1 + 1 + 2) + 2 * (size_t)n + 2 + 1024;
     SQCC_CUDA(cudaMalloc(&s->buf, total * sizeof(double)));
     SQCC_CUDA(cudaMemsetAsync(s->buf, 0, total * sizeof(double), ctx->stream));
     double *p = s->buf;
@@ -191,7 +202,8 @@ int sqcc_scf_setup(sqcc_ctx *ctx, const double *h_H, const double *h_X, int nspi
     s->FP = p; p += nn;
     s->CT = p; p += 2 * nn;
     s->W = p; p += 2 * (size_t)n;
-    s->E = p;
+    s->E = p; p += 2;
+    s->EP = p;
     SQCC_CUDA(cudaMemcpyAsync(s->H, h_H, nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     SQCC_CUDA(cudaMemcpyAsync(s->X, h_X, nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     SQCC_CUDA(cudaMalloc(&s->info, sizeof(int)));
@@ -230,9 +242,11 @@ int sqcc_scf_fock_energy(sqcc_ctx *ctx, double *h_e_elec)
     SQCC_CUDA(cudaMemsetAsync(s->E, 0, 2 * sizeof(double), ctx->stream));
     if (s->ksdft) SQCC_TRY(lda_vxc(ctx, s->D, s->nspin, s->VXC, s->E + 1, nullptr));
     SQCC_TRY(jk_build(ctx, s->D, s->nspin, s->ksdft ? 0 : 1, s->JK, s->ksdft ? nullptr : s->JK + nn));
-    scf_fock_energy_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(s->H, s->D, s->JK, s->JK + nn, s->VXC, s->nspin, s->ksdft,
-                                                                  nn, s->F, s->E);
-    ctx->launches++;
+    const int nparts = ctx->sm_count < 1024 ? ctx->sm_count : 1024;
+    scf_fock_energy_kernel<<<nparts, 256, 0, ctx->stream>>>(s->H, s->D, s->JK, s->JK + nn, s->VXC, s->nspin, s->ksdft, nn,
+                                                           s->F, s->EP);
+    scf_energy_sum_kernel<<<1, 32, 0, ctx->stream>>>(s->EP, nparts, s->E);
+    ctx->launches += 2;
     SQCC_CUDA(cudaGetLastError());
     double e[2];
     SQCC_CUDA(cudaMemcpyAsync(e, s->E, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

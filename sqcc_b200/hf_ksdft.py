@@ -140,6 +140,22 @@ class Calculator:
                     (qm_coordinates[i] - mm_coordinates[a]) * ANG_TO_BOHR)
         return energy
 
+    def _agree(self, value):
+        """Multi-GPU runs execute this driver once per rank.  Every rank must take the same |dE| < 1e-9 decision
+        (a rank that stops alone would leave the others waiting in the J/K exchange), so the energy of rank 0 is the
+        one all ranks use: LDA quantities are accumulated with floating-point atomics and may differ in the last
+        bits between ranks."""
+        eng = self.engine
+        if eng is None or eng.world == 1:
+            return value
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return value
+        t = torch.tensor([float(value)], dtype=torch.float64, device=eng.device)
+        dist.broadcast(t, 0, group=eng.group)
+        return float(t.item())
+
     # ------------------------------------------------------------------ SCF
     def scf(self):
         restricted = self.spin_orbital_treatment == "restricted"
@@ -207,7 +223,7 @@ class Calculator:
             engine.scf_setup(core_hamiltonian, orthogonalizer, 1 if restricted else 2, n_a, n_b, self.flag_ksdft)
             engine.scf_set_density(density)
             for step in range(MAX_SCF_ITER):
-                total_energy = engine.scf_fock_energy() + nuclear_repulsion
+                total_energy = self._agree(engine.scf_fock_energy() + nuclear_repulsion)
                 self.scf_energy_trace.append(float(total_energy))
                 print("SCF step %s: " % str(step + 1), total_energy, "Hartree")
                 if step > 0 and abs(old_total_energy - total_energy) < ENERGY_TOL:
@@ -250,7 +266,7 @@ class Calculator:
                     electronic = 0.5 * np.sum((density[0] + density[1]) * core_hamiltonian)
                     electronic += 0.5 * np.sum(density[0] * fock_a)
                     electronic += 0.5 * np.sum(density[1] * fock_b)
-            total_energy = electronic + nuclear_repulsion
+            total_energy = self._agree(electronic + nuclear_repulsion)
             self.scf_energy_trace.append(float(total_energy))
             print("SCF step %s: " % str(step + 1), total_energy, "Hartree")
             if step > 0 and abs(old_total_energy - total_energy) < ENERGY_TOL:
