@@ -24,11 +24,12 @@ __device__ __forceinline__ void gf_cp16(void *dst, const void *src, bool on)
 }
 
 // Copy tile `t` (rows t*128 .. +128 of phi[G][n], n even) into At[128][68]; rows past G are zero-filled.
+template <int TM = GF_TM>
 __device__ __forceinline__ void gf_load_tile(double *At, const double *__restrict__ phi, int64_t G, int n, int64_t t)
 {
     const int half = n >> 1;
-    const int chunks = GF_TM * half;
-    const int64_t g0 = t * GF_TM;
+    const int chunks = TM * half;
+    const int64_t g0 = t * TM;
     for (int c = threadIdx.x; c < chunks; c += GF_WARPS * 32) {
         const int r = c / half, cc = c - r * half;
         const bool on = g0 + r < G;
@@ -136,16 +137,16 @@ grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w
     }
 }
 
-template <int NSPIN>
-__global__ void __launch_bounds__(GF_WARPS * 32, 1)
+template <int NSPIN, int TMV>
+__global__ void __launch_bounds__(GF_WARPS * 32)
 grid_vxc_kernel(const double *__restrict__ phi, const double *__restrict__ wv, int64_t G, int n, double *__restrict__ V)
 {
     extern __shared__ __align__(128) double gsm[];
     double *At = gsm;                               // [2][128][68]
-    double *Ws = At + 2 * GF_TM * GF_LD;            // [2][NSPIN][128]
+    double *Ws = At + 2 * TMV * GF_LD;            // [2][NSPIN][128]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < 2 * GF_TM * GF_LD + 2 * NSPIN * GF_TM; e += GF_WARPS * 32) gsm[e] = 0.0;
-    const int64_t ntiles = (G + GF_TM - 1) / GF_TM;
+    for (int e = tid; e < 2 * TMV * GF_LD + 2 * NSPIN * TMV; e += GF_WARPS * 32) gsm[e] = 0.0;
+    const int64_t ntiles = (G + TMV - 1) / TMV;
     const int pt0 = 2 * (warp >> 1), qt0 = 4 * (warp & 1);   // this warp's 2 p-tiles x 4 q-tiles of the 64 x 64 output
     double acc[NSPIN][2][4][2];
 #pragma unroll
@@ -155,33 +156,33 @@ grid_vxc_kernel(const double *__restrict__ phi, const double *__restrict__ wv, i
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[s][i][j][0] = acc[s][i][j][1] = 0.0;
     auto load_w = [&](int b, int64_t t) {
-        for (int e = tid; e < NSPIN * GF_TM; e += GF_WARPS * 32) {
-            const int s = e / GF_TM, r = e % GF_TM;
-            const int64_t g = t * GF_TM + r;
-            Ws[(b * NSPIN + s) * GF_TM + r] = g < G ? wv[s * G + g] : 0.0;
+        for (int e = tid; e < NSPIN * TMV; e += GF_WARPS * 32) {
+            const int s = e / TMV, r = e % TMV;
+            const int64_t g = t * TMV + r;
+            Ws[(b * NSPIN + s) * TMV + r] = g < G ? wv[s * G + g] : 0.0;
         }
     };
     int buf = 0;
     __syncthreads();
     if ((int64_t)blockIdx.x < ntiles) {
-        gf_load_tile(At, phi, G, n, blockIdx.x);
+        gf_load_tile<TMV>(At, phi, G, n, blockIdx.x);
         load_w(0, blockIdx.x);
     }
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t tn = t + gridDim.x;
         __syncthreads();
         if (tn < ntiles) {
-            gf_load_tile(At + (buf ^ 1) * GF_TM * GF_LD, phi, G, n, tn);
+            gf_load_tile<TMV>(At + (buf ^ 1) * TMV * GF_LD, phi, G, n, tn);
             load_w(buf ^ 1, tn);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const double *A = At + buf * GF_TM * GF_LD;
-        const double *Wt = Ws + buf * NSPIN * GF_TM;
+        const double *A = At + buf * TMV * GF_LD;
+        const double *Wt = Ws + buf * NSPIN * TMV;
 #pragma unroll 2
-        for (int ks = 0; ks < GF_TM / 4; ++ks) {
+        for (int ks = 0; ks < TMV / 4; ++ks) {
             const int gq = 4 * ks + (lane & 3);           // grid point (k index) of this lane's fragment element
             const double *row = A + gq * GF_LD + (lane >> 2);
             double fa[2], fb[4];
@@ -191,7 +192,7 @@ grid_vxc_kernel(const double *__restrict__ phi, const double *__restrict__ wv, i
             for (int j = 0; j < 4; ++j) fb[j] = row[8 * (qt0 + j)];
 #pragma unroll
             for (int s = 0; s < NSPIN; ++s) {
-                const double sc = Wt[s * GF_TM + gq];
+                const double sc = Wt[s * TMV + gq];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const double a = fa[i] * sc;
@@ -242,11 +243,17 @@ static int launch_rho_lda(sqcc_ctx *ctx, const double *d_D, double c_pot, double
 template <int NSPIN>
 static int launch_vxc(sqcc_ctx *ctx, const double *d_wv, double *d_V)
 {
-    const size_t smem = sizeof(double) * (2 * GF_TM * GF_LD + 2 * NSPIN * GF_TM);
-    auto kern = grid_vxc_kernel<NSPIN>;
+    constexpr int TMV = 64;   // 64-point tiles: 70 KB per CTA, three CTAs per SM overlap each other's tile loads
+    const size_t smem = sizeof(double) * (2 * TMV * GF_LD + 2 * NSPIN * TMV);
+    auto kern = grid_vxc_kernel<NSPIN, TMV>;
     SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t ntiles = (ctx->G + GF_TM - 1) / GF_TM;
-    const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
+    int per_sm = 1;
+    SQCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GF_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    static const int vxc_ctas = getenv("SQCC_VXC_CTAS") ? atoi(getenv("SQCC_VXC_CTAS")) : 3;
+    if (per_sm > vxc_ctas) per_sm = vxc_ctas;
+    const int64_t ntiles = (ctx->G + TMV - 1) / TMV;
+    const int grid = (int)(ntiles < (int64_t)ctx->sm_count * per_sm ? ntiles : (int64_t)ctx->sm_count * per_sm);
     kern<<<grid, GF_WARPS * 32, smem, ctx->stream>>>(ctx->d_phi, d_wv, ctx->G, ctx->grid_n, d_V);
     ctx->launches++;
     SQCC_CUDA(cudaGetLastError());
