@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--variant", type=int, default=0, help="J/K kernel: 0 TMA pipeline, 2 direct-load, 1 simple")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: fused peer-memory exchange kernel (default) or finalize + NCCL all-reduce")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample time")
     return ap.parse_args()
 
 
@@ -142,7 +142,7 @@ def cpu_port_baseline(n, d, seconds):
         cjk.jk_packed_rows(rows, n, ij0, npair, d)
         reps += 1
         el = time.perf_counter() - t0
-        if el > seconds or reps >= 50:
+        if el > seconds or reps >= 400:
             break
     per_elem = el / (reps * elems)
     builds = 1.0 / (per_elem * nquad(n))
