@@ -39,18 +39,18 @@ __device__ __forceinline__ void pair_unrank_dev(int64_t ij, int &i, int &j)
     j = (int)(ij - t * (t + 1) / 2);
 }
 
-// S[pq][rs] = (pq|rs) for all pair indices: 32 x 32 tiles of the packed lower triangle are read along rows
-// (mostly contiguous in the native layout), written as they are and written transposed through shared memory.
+// S[pq][rs] = (pq|rs) for all pair indices: 128 x 32 tiles of the packed lower triangle are read along rows (mostly
+// contiguous in the native layout), written as they are and written transposed through shared memory.  Tall tiles
+// amortise the per-thread index work (pair unranking of the column, sub-row offset) over 16 rows per thread.
+constexpr int SYM_TR = 128, SYM_TC = 32;
+
 __global__ void __launch_bounds__(256) symmetrize_pairs_kernel(const double *__restrict__ P,
                                                                const int64_t *__restrict__ rowoff, int64_t npair,
-                                                               int64_t ntile, double *__restrict__ S)
+                                                               double *__restrict__ S)
 {
-    __shared__ double tile[32][33];
-    // blockIdx.x enumerates tile pairs (tr >= tc)
-    const int64_t b = blockIdx.x;
-    int tr, tc;
-    pair_unrank_dev(b, tr, tc);
-    const int64_t R0 = (int64_t)tr * 32, C0 = (int64_t)tc * 32;
+    __shared__ double tile[SYM_TR][SYM_TC + 1];
+    const int64_t R0 = (int64_t)blockIdx.y * SYM_TR, C0 = (int64_t)blockIdx.x * SYM_TC;
+    if (C0 > R0 + SYM_TR - 1) return;   // tile entirely above the diagonal
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t rs = C0 + lane;
     int k = 0, l = 0;
@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(256) symmetrize_pairs_kernel(const double *__r
     // (i, j) of this warp's first row, then stepped by 8 rows at a time (no sqrt per row)
     int i = 0, j = 0;
     pair_unrank_dev(R0 + warp < npair ? R0 + warp : npair - 1, i, j);
-    for (int r = warp; r < 32; r += 8) {
+#pragma unroll 4
+    for (int r = warp; r < SYM_TR; r += 8) {
         const int64_t pq = R0 + r;
         double v = 0.0;
         if (pq < npair && rs <= pq) {
@@ -73,12 +74,16 @@ __global__ void __launch_bounds__(256) symmetrize_pairs_kernel(const double *__r
         while (j > i) { j -= i + 1; ++i; }
     }
     __syncthreads();
-    for (int r = warp; r < 32; r += 8) {
-        // element (pq = R0 + lane, rs = C0 + r) goes to S[rs][pq]
-        const int64_t pq = R0 + lane, rs2 = C0 + r;
-        if (pq < npair && rs2 < pq) S[rs2 * npair + pq] = tile[lane][r];
+    for (int c = warp; c < SYM_TC; c += 8) {
+        // elements (pq = R0 + lane + 32 m, rs = C0 + c) go to S[rs][pq]
+        const int64_t rs2 = C0 + c;
+        if (rs2 >= npair) break;
+#pragma unroll
+        for (int m = 0; m < SYM_TR / 32; ++m) {
+            const int64_t pq = R0 + lane + 32 * m;
+            if (pq < npair && rs2 < pq) S[rs2 * npair + pq] = tile[lane + 32 * m][c];
+        }
     }
-    (void)ntile;
 }
 
 int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2, const double *d_C3, int n3,
@@ -95,10 +100,9 @@ int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2,
     double *S = ctx->d_mp2work, *T1 = S + s_sz, *T2 = T1 + t13, *T3 = T1;
 
     {   // symmetrised pair matrix
-        const int64_t ntile = (npair + 31) / 32;
-        const int64_t nblk = ntile * (ntile + 1) / 2;
-        SQCC_REQUIRE(nblk < ((int64_t)1 << 31), "pair matrix too large for one launch");
-        symmetrize_pairs_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, npair, ntile, S);
+        const dim3 sgrid((unsigned)((npair + SYM_TC - 1) / SYM_TC), (unsigned)((npair + SYM_TR - 1) / SYM_TR));
+        SQCC_REQUIRE(sgrid.y <= 65535, "pair matrix too large for one launch");
+        symmetrize_pairs_kernel<<<sgrid, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, npair, S);
         ctx->launches += 1;
         SQCC_CUDA(cudaGetLastError());
     }
