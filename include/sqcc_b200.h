@@ -9,8 +9,9 @@
  * Conventions
  *   - every function returns 0 on success, a negative sqcc_status on error; sqcc_last_error() returns
  *     a thread-local message.  No exceptions cross the ABI.
- *   - one sqcc_ctx drives ONE device (one process per GPU; cross-rank sums are done by the caller with
- *     torch.distributed/NCCL on the output buffers).  A context is not thread-safe.
+ *   - one sqcc_ctx drives ONE device (one process per GPU).  A context is not thread-safe.  The cross-rank sum of the
+ *     partial J/K of a sharded tensor is done inside sqcc_jk_build once a peer group is attached (sqcc_comm_*); without
+ *     one the caller all-reduces the output buffers itself (torch.distributed / NCCL).
  *   - "d_" pointers are device pointers owned by the CALLER (e.g. torch tensors' data_ptr()); the
  *     library never frees them.  "h_" pointers are host pointers.  Scratch lives in the context.
  *   - all matrices are row-major float64.  D / J / K / Vxc are dense [N,N] (or [nspin,N,N]).
@@ -121,14 +122,17 @@ int sqcc_jk_trace(sqcc_ctx *ctx, int enable, uint64_t *h_out, int max_warps);
  *   one process, several contexts: sqcc_comm_attach_local(ctxs, world); contexts on distinct devices then use
  *     sqcc_jk_build as above; contexts sharing ONE device (tests) must run sqcc_jk_partial on each and finish with a
  *     single sqcc_jk_reduce_local launch (kernels that wait for each other cannot be separate launches on one GPU).
- * Every rank of a group must issue the same sequence of builds.  sqcc_comm_status: < 0 after a barrier timeout,
- * else the group size (0: none). */
+ * Every rank of a group must issue the same sequence of builds.  sqcc_comm_status: < 0 after a barrier timeout
+ * (the timed-out rank publishes nothing, tells its peers through the barrier flags, and every rank's J/K of that build
+ * are NaN), else the group size (0: none). */
 #define SQCC_COMM_HANDLE_BYTES 64
 int sqcc_comm_export(sqcc_ctx *ctx, void *handle /* SQCC_COMM_HANDLE_BYTES */);
 int sqcc_comm_attach(sqcc_ctx *ctx, int world, int rank, const void *handles /* world * SQCC_COMM_HANDLE_BYTES */);
 int sqcc_comm_attach_local(sqcc_ctx **ctxs, int world);
 int sqcc_comm_detach(sqcc_ctx *ctx);
 int sqcc_comm_status(sqcc_ctx *ctx);
+/* The status word is sticky: after a failed exchange (every rank's J/K are NaN-filled) clear it before reuse. */
+int sqcc_comm_reset_status(sqcc_ctx *ctx);
 /* enabled = 0: sqcc_jk_build returns this rank's partials although a group is attached (A/B against an all-reduce). */
 int sqcc_comm_set_enabled(sqcc_ctx *ctx, int enabled);
 /* Tuning aid: globaltimer (ns) at the phase boundaries of the last exchange launch on this rank: start, after barrier A,
@@ -172,6 +176,13 @@ int sqcc_ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, in
 int sqcc_scf_setup(sqcc_ctx *ctx, const double *h_H, const double *h_X, int nspin, int n_occ_a, int n_occ_b, int ksdft);
 int sqcc_scf_set_density(sqcc_ctx *ctx, const double *h_D);
 int sqcc_scf_fock_energy(sqcc_ctx *ctx, double *h_e_elec);
+/* The two halves of sqcc_scf_fock_energy for a sharded tensor whose partial J/K are summed by the CALLER (NCCL
+ * all-reduce instead of the fused peer exchange): sqcc_scf_jk leaves [J; K...] of the resident density in a
+ * library-owned device buffer (*d_jk, *n_doubles doubles; this rank's partials when nothing sums them), the caller
+ * all-reduces it in place, sqcc_scf_finish builds the Fock matrices and the energy from it.  sqcc_scf_fock_energy
+ * itself refuses a sharded tensor without an active peer exchange (it would use partial matrices). */
+int sqcc_scf_jk(sqcc_ctx *ctx, void **d_jk, int64_t *n_doubles);
+int sqcc_scf_finish(sqcc_ctx *ctx, double *h_e_elec);
 int sqcc_scf_update(sqcc_ctx *ctx);
 int sqcc_scf_get(sqcc_ctx *ctx, double *h_D, double *h_Ct, double *h_eps);
 

@@ -34,6 +34,9 @@ def lib():
         _lib.sqcc_oracle_synth_rows.argtypes = [ctypes.c_int64, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, _dp]
         _lib.sqcc_oracle_jk_packed_rows.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp,
                                                     ctypes.c_int, ctypes.c_int, _dp, _dp]
+        _lib.sqcc_oracle_mp2_entries_synth.argtypes = [ctypes.c_int64, ctypes.c_uint64, _dp, ctypes.c_int64,
+                                                       ctypes.c_int64, _ip, _ip, ctypes.c_int64, _dp]
+        _lib.sqcc_oracle_synth_slabs_rs.argtypes = [ctypes.c_int64, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, _dp]
     return _lib
 
 
@@ -125,3 +128,22 @@ def jk_packed_segments(n, seed, segments, d, want_k=True):
     if want_k and d.ndim == 2:
         k = k[0]
     return j, k
+
+
+def mp2_entries_synth(n, seed, c, i, j, ab):
+    """(ia|jb) of the synthetic tensor for one occupied MO pair (i, j) and MO column pairs ab = [(a, b), ...], by the
+    reference's four nested np.dot steps (mp2.py:123-170).  `c` is the full [N,N] AO x MO matrix; a, b are MO columns."""
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    ab = np.asarray(ab, dtype=np.int64).reshape(-1, 2)
+    ca, cb = np.ascontiguousarray(ab[:, 0]), np.ascontiguousarray(ab[:, 1])
+    out = np.zeros(len(ab))
+    lib().sqcc_oracle_mp2_entries_synth(n, seed, _p(c), int(i), int(j), ca.ctypes.data_as(_ip), cb.ctypes.data_as(_ip),
+                                        len(ab), _p(out))
+    return out
+
+
+def synth_slabs_rs(n, seed, rs0, rs1):
+    """ERI[:, :, r, s] for the canonical pairs rs in [rs0, rs1) of the synthetic tensor: [rs1 - rs0, N, N]."""
+    out = np.empty((rs1 - rs0, n, n))
+    lib().sqcc_oracle_synth_slabs_rs(n, seed, rs0, rs1, _p(out))
+    return out

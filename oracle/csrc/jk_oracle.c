@@ -230,3 +230,58 @@ void sqcc_oracle_jk_packed_rows(const double *packed, int64_t n, int64_t ij0, in
     free(acc);
     free(dtot);
 }
+
+/* ---- MP2 AO->MO quarter transforms on the synthetic tensor (mp2.py:123-170), config-size oracle ----------------
+ * (ia|jb) for ONE occupied pair (i, j) and a list of virtual pairs (a, b), evaluated with the reference's nesting of
+ * the four np.dot steps restricted to the indices that are needed:
+ *   temp1[i,q,r,s] = C[:,i] . ERI[:,q,r,s]      :123-130      temp2[i,q,j,s] = C[:,j] . temp1[i,q,:,s]   :136-143
+ *   temp3[i,a,j,s] = C[:,a] . temp2[i,:,j,s]    :149-156      iajb[i,a,j,b]  = C[:,b] . temp3[i,a,j,:]   :162-170
+ * C is the [N,N] AO x MO matrix (row-major); ci, cj, ca[], cb[] are MO column indices.  The tensor is generated
+ * lazily (synth_any), so N = 222 needs no 19 GB host array.  Sums are long double (oracle accuracy). */
+void sqcc_oracle_mp2_entries_synth(int64_t n, uint64_t seed, const double *C, int64_t ci, int64_t cj, const int64_t *ca,
+                                   const int64_t *cb, int64_t cnt, double *out)
+{
+    double *t2 = (double *)malloc(sizeof(double) * n * n); /* temp2[i, q, j, s] for the fixed (i, j) */
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t qs = 0; qs < n * n; ++qs) {
+        int64_t q = qs / n, s = qs % n;
+        long double acc = 0.0L;
+        for (int64_t r = 0; r < n; ++r) {
+            long double t1 = 0.0L;
+            for (int64_t p = 0; p < n; ++p) t1 += (long double)(C[p * n + ci] * synth_any(n, seed, p, q, r, s));
+            acc += (long double)C[r * n + cj] * t1;
+        }
+        t2[qs] = (double)acc;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < cnt; ++e) {
+        long double acc = 0.0L;
+        for (int64_t s = 0; s < n; ++s) {
+            long double t3 = 0.0L;
+            for (int64_t q = 0; q < n; ++q) t3 += (long double)(C[q * n + ca[e]] * t2[q * n + s]);
+            acc += (long double)C[s * n + cb[e]] * t3;
+        }
+        out[e] = (double)acc;
+    }
+    free(t2);
+}
+
+/* Slabs ERI[:, :, r, s] ([N, N] each, plain integral values) of the synthetic tensor for the canonical pairs
+ * rs in [rs0, rs1): operands of the chunked einsum restatement of the quarter transforms (oracle/mp2_ref.py). */
+void sqcc_oracle_synth_slabs_rs(int64_t n, uint64_t seed, int64_t rs0, int64_t rs1, double *out)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t rs = rs0; rs < rs1; ++rs) {
+        int64_t r = (int64_t)((sqrt(8.0 * (double)rs + 1.0) - 1.0) / 2.0);
+        while (r * (r + 1) / 2 > rs) --r;
+        while ((r + 1) * (r + 2) / 2 <= rs) ++r;
+        int64_t s = rs - r * (r + 1) / 2;
+        double *slab = out + (rs - rs0) * n * n;
+        for (int64_t p = 0; p < n; ++p)
+            for (int64_t q = 0; q <= p; ++q) {
+                double v = synth_any(n, seed, p, q, r, s);
+                slab[p * n + q] = v;
+                slab[q * n + p] = v;
+            }
+    }
+}

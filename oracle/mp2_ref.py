@@ -73,3 +73,28 @@ def mp2_corr(eri, c, eps, n_occ, loops=False):
         return energy_loop(iajb, e_occ, e_virt), iajb
     iajb = transform_einsum(eri, c_occ, c_virt)
     return energy_einsum(iajb, e_occ, e_virt), iajb
+
+
+def mp2_corr_synth_chunked(n, seed, c, eps, n_occ, chunk=512):
+    """Config-size restatement (N = 222 needs no 19 GB tensor): the four quarter transforms of mp2.py:123-170 as GEMMs
+    over chunks of canonical (r, s) pairs of the lazily generated synthetic tensor, then the energy sum of :240-254.
+    Returns (E_corr, iajb [n_occ, n_virt, n_occ, n_virt])."""
+    from . import cjk
+    c_occ, c_virt = np.ascontiguousarray(c[:, :n_occ]), np.ascontiguousarray(c[:, n_occ:])
+    nv = n - n_occ
+    npair = n * (n + 1) // 2
+    y = np.empty((npair, n_occ, nv))                    # (ia|rs) for canonical rs
+    for rs0 in range(0, npair, chunk):
+        rs1 = min(npair, rs0 + chunk)
+        x = cjk.synth_slabs_rs(n, seed, rs0, rs1)       # [c, p, q]
+        t1 = np.matmul(c_occ.T[None], x)                # [c, i, q]    temp1 (:123-130)
+        y[rs0:rs1] = np.matmul(t1, c_virt[None])        # [c, i, a]    (contract q with C_virt, :149-156)
+    r, s = np.tril_indices(n)
+    iajb = np.empty((n_occ, nv, n_occ, nv))
+    for i in range(n_occ):
+        z = np.zeros((nv, n, n))
+        z[:, r, s] = y[:, i, :].T
+        z[:, s, r] = y[:, i, :].T
+        w = np.matmul(c_occ.T[None], z)                 # [a, j, s]    (:136-143)
+        iajb[i] = np.matmul(w, c_virt[None])            # [a, j, b]    (:162-170)
+    return energy_einsum(iajb, eps[:n_occ], eps[n_occ:]), iajb

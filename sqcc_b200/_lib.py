@@ -44,6 +44,7 @@ SIGNATURES = {
     "sqcc_comm_attach_local": (c_int, [ctypes.POINTER(c_void_p), c_int]),
     "sqcc_comm_detach": (c_int, [c_void_p]),
     "sqcc_comm_status": (c_int, [c_void_p]),
+    "sqcc_comm_reset_status": (c_int, [c_void_p]),
     "sqcc_comm_set_enabled": (c_int, [c_void_p, c_int]),
     "sqcc_comm_stamps": (c_int, [c_void_p, c_void_p]),
     "sqcc_jk_partial": (c_int, [c_void_p, c_void_p, c_int, c_int]),
@@ -60,6 +61,8 @@ SIGNATURES = {
     "sqcc_scf_setup": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
     "sqcc_scf_set_density": (c_int, [c_void_p, c_void_p]),
     "sqcc_scf_fock_energy": (c_int, [c_void_p, c_double_p]),
+    "sqcc_scf_jk": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_int64)]),
+    "sqcc_scf_finish": (c_int, [c_void_p, c_double_p]),
     "sqcc_scf_update": (c_int, [c_void_p]),
     "sqcc_scf_get": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "sqcc_get_timings": (c_int, [c_void_p, c_double_p, c_int]),

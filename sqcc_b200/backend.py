@@ -67,6 +67,19 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class _RawDeviceBuffer:
+    """A library-owned float64 device buffer exposed through __cuda_array_interface__ (no copy, no ownership)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _device_view(ptr, count, device):
+    with torch.cuda.device(device):
+        return torch.as_tensor(_RawDeviceBuffer(ptr, count), device=device)
+
+
 class FockEngine:
     """J/K, LDA grid quadrature and MP2 transforms on one B200; mirrors the loop nests of hf_ksdft.py/mp2.py."""
 
@@ -78,7 +91,8 @@ class FockEngine:
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         self.exchange = exchange
-        self._p2p = False
+        self._p2p = False      # the fused exchange is active: sqcc_jk_build returns the FULL J/K
+        self._mapped = False   # the peers' regions are mapped (stays true while the exchange is toggled off)
         if not torch.cuda.is_available():
             raise _lib.SqccError("sqcc_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
@@ -101,8 +115,8 @@ class FockEngine:
         """Unmap the peers' regions; nobody may free its region before every rank has unmapped it (barrier).
         collective=False (garbage collection / interpreter exit) skips the barrier: a destructor must not block on
         ranks that may never arrive."""
-        if self._p2p:
-            self._p2p = False
+        if self._mapped:
+            self._p2p = self._mapped = False
             self.lib.sqcc_comm_detach(self.ctx)
             import torch.distributed as dist
             if collective and dist.is_available() and dist.is_initialized():
@@ -160,11 +174,11 @@ class FockEngine:
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 1:
-            self._p2p = True
+            self._p2p = self._mapped = True
             return
         self.lib.sqcc_comm_detach(self.ctx)
         dist.barrier(group=self.group)
-        self._p2p = False
+        self._p2p = self._mapped = False
         self.exchange = "nccl"
         if self.rank == 0:
             warnings.warn("sqcc_b200: peer-memory exchange unavailable (" + (err or "a rank failed to map its peers") +
@@ -260,6 +274,8 @@ class FockEngine:
         if out is None:
             out = torch.empty((1 + (nspin if want_k else 0), n, n), dtype=torch.float64, device=self.device)
         self._use_stream()
+        if self._p2p:
+            self.comm_check()   # mapped host word, no sync: a failed exchange of an EARLIER build surfaces here
         _lib.check(self.lib.sqcc_jk_build(self.ctx, _ptr(d), nspin, int(want_k), _ptr(out[0]),
                                           _ptr(out[1]) if want_k else None))
         if not self._p2p:
@@ -272,7 +288,7 @@ class FockEngine:
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         if exchange == "p2p" and not self._p2p and self._group_size() > 1:
-            if _lib.check(self.lib.sqcc_comm_status(self.ctx)) > 1:
+            if self._mapped:
                 _lib.check(self.lib.sqcc_comm_set_enabled(self.ctx, 1))
                 self._p2p = True
             else:
@@ -283,8 +299,12 @@ class FockEngine:
         self.exchange = exchange
 
     def comm_check(self):
-        """Raises if a peer barrier of the fused exchange timed out (reads a mapped host word; no sync)."""
+        """Raises if a peer barrier of the fused exchange timed out (reads a mapped host word; no sync).  After a
+        failure every rank's J/K of that build are NaN; comm_reset() clears the sticky status."""
         return _lib.check(self.lib.sqcc_comm_status(self.ctx))
+
+    def comm_reset(self):
+        _lib.check(self.lib.sqcc_comm_reset_status(self.ctx))
 
     def pinned(self, *shape):
         """A page-locked float64 numpy array (torch owns the allocation): buffers handed to jk() that are pinned
@@ -313,8 +333,14 @@ class FockEngine:
             if self._p2p:
                 self.comm_check()
         else:
-            out = self.jk_device(torch.from_numpy(d).to(self.device), want_k).cpu().numpy()
-            j, k = out[0], (out[1:] if want_k else None)
+            res = self.jk_device(torch.from_numpy(d).to(self.device), want_k).cpu().numpy()
+            j, k = res[0], (res[1:] if want_k else None)
+            if out is not None:   # fill the caller's buffers on this branch too
+                out[0][...] = j
+                j = out[0]
+                if want_k:
+                    out[1][...] = k
+                    k = out[1]
         if want_k and d.ndim == 2:
             k = k[0]
         return j, k
@@ -333,10 +359,18 @@ class FockEngine:
         _lib.check(self.lib.sqcc_scf_set_density(self.ctx, d.ctypes.data_as(ctypes.c_void_p)))
 
     def scf_fock_energy(self):
-        """Fock build for the resident density; returns the electronic energy (the only per-iteration D2H)."""
+        """Fock build for the resident density; returns the electronic energy (the only per-iteration D2H).
+        On a sharded tensor without the fused peer exchange the partial [J; K] are all-reduced here (NCCL) between the
+        two halves of the step, so the Fock matrix never sees a rank's partial matrices."""
         e = ctypes.c_double()
         self._use_stream()
-        _lib.check(self.lib.sqcc_scf_fock_energy(self.ctx, ctypes.byref(e)))
+        if self._group_size() > 1 and not self._p2p:
+            ptr, cnt = ctypes.c_void_p(), ctypes.c_int64()
+            _lib.check(self.lib.sqcc_scf_jk(self.ctx, ctypes.byref(ptr), ctypes.byref(cnt)))
+            reduce_partials(_device_view(ptr.value, cnt.value, self.device), self.group)
+            _lib.check(self.lib.sqcc_scf_finish(self.ctx, ctypes.byref(e)))
+        else:
+            _lib.check(self.lib.sqcc_scf_fock_energy(self.ctx, ctypes.byref(e)))
         return e.value
 
     def scf_update(self):
@@ -432,6 +466,8 @@ class FockEngine:
 
     def synchronize(self):
         _lib.check(self.lib.sqcc_ctx_synchronize(self.ctx))
+        if self._p2p:
+            self.comm_check()
 
 
 class FockGroup:

@@ -13,12 +13,16 @@
 //   phase 2     local: J = J~ + J~^T, K = K~ + K~^T from the local result buffer into the caller's J/K
 //
 // Every element is summed by exactly one rank in a fixed order, so all ranks end with bit-identical J/K.
-// Spins are bounded (COMM_TIMEOUT_NS); a timeout is reported through a mapped host word (sqcc_comm_status).
+// Spins are bounded (COMM_TIMEOUT_NS).  A rank whose wait times out does NOT carry on with incomplete data: it skips
+// its phase-1 stores, releases barrier B with COMM_FAIL_BIT set in the flag value (so that every peer learns of the
+// failure in the same epoch), every rank that saw a failure fills its J/K with NaN, and the sticky status word (mapped
+// host memory, sqcc_comm_status / sqcc_comm_reset_status) is raised on each of them.
 #include "common.cuh"
 
 namespace sqcc {
 
 constexpr unsigned long long COMM_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long COMM_FAIL_BIT = 1ull << 63;   // flag value = epoch | COMM_FAIL_BIT: the sender gave up
 
 struct CommRank {   // one rank's view of the group (device copy in sqcc_ctx::comm.d_view)
     const double *acc[COMM_MAXW];           // every rank's accumulators [3][N][ldd]
@@ -63,15 +67,24 @@ __device__ __forceinline__ void st_peer2(double *p, double2 v)
 {
     asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
-__device__ __forceinline__ void wait_flag(const unsigned long long *p, unsigned long long epoch, int *status)
+// Returns false when the wait timed out or the sender flagged a failure for this epoch.
+__device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned long long epoch, int *status)
 {
     const unsigned long long t0 = comm_now();
-    while (ld_acquire_sys(p) < epoch) {
+    for (;;) {
+        const unsigned long long v = ld_acquire_sys(p);
+        if ((v & ~COMM_FAIL_BIT) >= epoch) {
+            if ((v & COMM_FAIL_BIT) && (v & ~COMM_FAIL_BIT) == epoch) {
+                *status = 3;   // a peer reported a failed exchange
+                return false;
+            }
+            return true;
+        }
         __nanosleep(200);   // the GPUs run at their power cap: a waiting rank should not burn it polling
         if (comm_now() - t0 > COMM_TIMEOUT_NS) {
             *status = 1;
             __threadfence_system();
-            break;
+            return false;
         }
     }
 }
@@ -87,18 +100,23 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
     const int nplanes = want_k ? 1 + nspin : 1;
 
     const bool stamp = blockIdx.x == 0 && tid == 0;
+    __shared__ int s_fail;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
     if (stamp) cr.stamps[0] = comm_now();
     // ---- barrier A: my accumulators are complete (the J/K kernel precedes this launch on the stream)
     if (blockIdx.x == 0 && tid < world) {
         __threadfence_system();
         st_release_sys(cr.flags[tid] + me, epoch);
     }
-    if (tid < world) wait_flag(cr.flags[me] + tid, epoch, cr.status);
+    if (tid < world && !wait_flag(cr.flags[me] + tid, epoch, cr.status)) s_fail = 1;
     __syncthreads();
+    const bool failed_a = s_fail != 0;
     if (stamp) cr.stamps[1] = comm_now();
 
-    // ---- phase 1: reduce slice `me` of every rank's accumulators, broadcast the sums
-    {
+    // ---- phase 1: reduce slice `me` of every rank's accumulators, broadcast the sums (skipped after a failed barrier:
+    // the peers' accumulators may be incomplete, nothing derived from them is published)
+    if (!failed_a) {
         const size_t total2 = (size_t)nplanes * nl / 2;   // 16-byte units (ldd is a multiple of 4)
         const size_t s0 = total2 * (size_t)me / world, s1 = total2 * (size_t)(me + 1) / world;
         for (size_t t = s0 + (size_t)blockIdx.x * blockDim.x + tid; t < s1; t += (size_t)gridDim.x * blockDim.x) {
@@ -132,6 +150,7 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
                 __nanosleep(100);
                 if (comm_now() - t0 > COMM_TIMEOUT_NS) {
                     *cr.status = 2;
+                    s_fail = 1;
                     break;
                 }
             }
@@ -139,10 +158,12 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
             cr.stamps[3] = comm_now();
         }
         __syncthreads();
-        if (tid < world) st_release_sys(cr.flags[tid] + COMM_MAXW + me, epoch);
+        // release barrier B; a rank that gave up says so in the flag, so every peer poisons its result in this epoch
+        if (tid < world) st_release_sys(cr.flags[tid] + COMM_MAXW + me, s_fail ? (epoch | COMM_FAIL_BIT) : epoch);
     }
-    if (tid < world) wait_flag(cr.flags[me] + COMM_MAXW + tid, epoch, cr.status);
+    if (tid < world && !wait_flag(cr.flags[me] + COMM_MAXW + tid, epoch, cr.status)) s_fail = 1;
     __syncthreads();
+    const bool failed = s_fail != 0;
     if (stamp) cr.stamps[4] = comm_now();
 
     // ---- phase 2 (local): symmetrise into the caller's J / K.  Four elements per thread with all loads issued before
@@ -169,14 +190,15 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
                     }
                 }
             }
+            const double poison = __longlong_as_double(0x7ff8000000000000ll);   // NaN: a failed exchange never looks valid
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const size_t idx = base + u * stride;
                 if (idx < nn) {
-                    cr.J[idx] = jv[u];
+                    cr.J[idx] = failed ? poison : jv[u];
                     if (want_k) {
-                        cr.K[idx] = ka[u];
-                        if (nspin == 2) cr.K[nn + idx] = kb[u];
+                        cr.K[idx] = failed ? poison : ka[u];
+                        if (nspin == 2) cr.K[nn + idx] = failed ? poison : kb[u];
                     }
                 }
             }
@@ -197,6 +219,7 @@ static void comm_close_peers(sqcc_ctx *ctx)
     for (int g = 0; g < COMM_MAXW; ++g) c.peer_base[g] = nullptr;
     c.view_valid = false;
     c.attached = false;
+    c.enabled = true;   // a toggle set for an old mapping must not outlive it (sqcc_comm_set_enabled)
     c.ipc = false;
     c.world = 1;
     c.rank = 0;
@@ -402,6 +425,13 @@ int sqcc_comm_status(sqcc_ctx *ctx)
         return SQCC_ERR_CUDA;
     }
     return ctx->comm.attached ? ctx->comm.world : 0;
+}
+
+int sqcc_comm_reset_status(sqcc_ctx *ctx)
+{
+    SQCC_REQUIRE(ctx, "null ctx");
+    if (ctx->comm.h_status) *ctx->comm.h_status = 0;
+    return SQCC_OK;
 }
 
 int sqcc_jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)

@@ -233,15 +233,29 @@ int sqcc_scf_set_density(sqcc_ctx *ctx, const double *h_D)
     return SQCC_OK;
 }
 
-int sqcc_scf_fock_energy(sqcc_ctx *ctx, double *h_e_elec)
+// The resident density's J/K (and LDA V_xc) into the state's [J; K...] buffer.  On a sharded tensor whose partials
+// are NOT summed by the fused exchange (no peer group, or sqcc_comm_set_enabled(0)) the buffer holds this rank's
+// PARTIAL matrices: the caller must all-reduce *d_jk (n_doubles doubles) before sqcc_scf_finish.
+int sqcc_scf_jk(sqcc_ctx *ctx, void **d_jk, int64_t *n_doubles)
+{
+    SQCC_REQUIRE(ctx && ctx->scf, "sqcc_scf_setup first");
+    ScfState *s = ctx->scf;
+    const size_t nn = (size_t)s->n * s->n;
+    SQCC_CUDA(cudaMemsetAsync(s->E, 0, 2 * sizeof(double), ctx->stream));
+    if (s->ksdft) SQCC_TRY(lda_vxc(ctx, s->D, s->nspin, s->VXC, s->E + 1, nullptr));
+    SQCC_TRY(jk_build(ctx, s->D, s->nspin, s->ksdft ? 0 : 1, s->JK, s->ksdft ? nullptr : s->JK + nn));
+    if (d_jk) *d_jk = s->JK;
+    if (n_doubles) *n_doubles = (int64_t)((s->ksdft ? 1 : 1 + s->nspin) * nn);
+    return SQCC_OK;
+}
+
+// Fock matrices + electronic energy from the (complete) J/K in the state's buffer.
+int sqcc_scf_finish(sqcc_ctx *ctx, double *h_e_elec)
 {
     SQCC_REQUIRE(ctx && ctx->scf && h_e_elec, "sqcc_scf_setup first");
     ScfState *s = ctx->scf;
     const int n = s->n;
     const size_t nn = (size_t)n * n;
-    SQCC_CUDA(cudaMemsetAsync(s->E, 0, 2 * sizeof(double), ctx->stream));
-    if (s->ksdft) SQCC_TRY(lda_vxc(ctx, s->D, s->nspin, s->VXC, s->E + 1, nullptr));
-    SQCC_TRY(jk_build(ctx, s->D, s->nspin, s->ksdft ? 0 : 1, s->JK, s->ksdft ? nullptr : s->JK + nn));
     const int nparts = ctx->sm_count < 1024 ? ctx->sm_count : 1024;
     scf_fock_energy_kernel<<<nparts, 256, 0, ctx->stream>>>(s->H, s->D, s->JK, s->JK + nn, s->VXC, s->nspin, s->ksdft, nn,
                                                            s->F, s->EP);
@@ -260,6 +274,17 @@ int sqcc_scf_fock_energy(sqcc_ctx *ctx, double *h_e_elec)
         return SQCC_ERR_CUDA;
     }
     return SQCC_OK;
+}
+
+int sqcc_scf_fock_energy(sqcc_ctx *ctx, double *h_e_elec)
+{
+    SQCC_REQUIRE(ctx && ctx->scf && h_e_elec, "sqcc_scf_setup first");
+    // a shard's partial J/K must never reach the Fock matrix: without the fused exchange the caller has to sum the
+    // partials itself (sqcc_scf_jk -> all-reduce -> sqcc_scf_finish)
+    const bool summed = ctx->whole || (ctx->comm.attached && ctx->comm.enabled && ctx->comm.world > 1 && !ctx->comm.same_device);
+    SQCC_REQUIRE(summed, "sharded ERI without the fused peer exchange: use sqcc_scf_jk + all-reduce + sqcc_scf_finish");
+    SQCC_TRY(sqcc_scf_jk(ctx, nullptr, nullptr));
+    return sqcc_scf_finish(ctx, h_e_elec);
 }
 
 int sqcc_scf_update(sqcc_ctx *ctx)

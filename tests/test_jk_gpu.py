@@ -110,6 +110,37 @@ def test_benzene_size_222(engine):
     ju, ku = engine.jk(np.stack([0.5 * d, 0.5 * d]))
     assert np.abs(ju - j).max() <= TOL and np.abs(2.0 * ku[0] - k).max() <= TOL
     assert np.abs(ku[0] - ku[1]).max() <= TOL
+    # dual-density pass with genuinely different spin densities (hf_ksdft.py:510-535), whole matrices
+    du = synth.synth_density_uhf(n, 23, 19, 3)
+    ju, ku = engine.jk(du)
+    jr, kr = cjk.jk_packed(packed, n, du)
+    assert np.abs(ju - jr).max() <= TOL and np.abs(ku - kr).max() <= TOL
+    je, ke = cjk.jk_entries(cjk.SRC_PACKED, packed, n, seed, du, ent)
+    for t, (p, q) in enumerate(ent):
+        assert abs(ju[p, q] - je[t]) <= TOL and abs(ku[0][p, q] - ke[0][t]) <= TOL and abs(ku[1][p, q] - ke[1][t]) <= TOL
+    jo, ko = engine.jk(du, want_k=False)
+    assert ko is None and np.abs(jo - jr).max() <= TOL
+
+
+def test_benzene_size_264(engine):
+    """The basis size BASELINE.json literally names for configs[1] (~264): RHF and UHF (Da != Db) whole matrices vs the
+    C oracle on the canonical packed tensor, plus reference-loop-nest entries."""
+    n, seed = 264, 20261019
+    d = synth.synth_density_rhf(n, 21, 7)
+    du = synth.synth_density_uhf(n, 22, 20, 9)
+    engine.attach_eri_synth(n, seed)
+    j, k = engine.jk(d)
+    ju, ku = engine.jk(du)
+    packed = cjk.synth_canonical(n, seed)
+    jr, kr = cjk.jk_packed(packed, n, d)
+    assert np.abs(j - jr).max() <= TOL and np.abs(k - kr).max() <= TOL
+    jr, kr = cjk.jk_packed(packed, n, du)
+    assert np.abs(ju - jr).max() <= TOL and np.abs(ku - kr).max() <= TOL
+    ent = [(0, 0), (263, 263), (263, 0), (131, 132), (17, 250), (250, 17), (1, 0), (263, 262)]
+    je, ke = cjk.jk_entries(cjk.SRC_PACKED, packed, n, seed, d, ent)
+    for t, (p, q) in enumerate(ent):
+        assert abs(j[p, q] - je[t]) <= TOL and abs(k[p, q] - ke[t]) <= TOL
+    engine.attach_eri_synth(4, 1)
 
 
 @pytest.mark.parametrize("n,world", [(10, 2), (37, 3), (70, 8), (5, 8)])
@@ -249,4 +280,13 @@ def test_anthracene_size_494(engine):
     assert np.abs(ju - j).max() <= TOL and np.abs(2.0 * ku[0] - k).max() <= TOL and np.abs(ku[0] - ku[1]).max() <= TOL
     jo, ko = engine.jk(d, want_k=False)
     assert ko is None and np.abs(jo - j).max() <= TOL
+    # dual-density pass with Da != Db (hf_ksdft.py:510-535): sampled entries by the reference loop nest
+    du = synth.synth_density_uhf(n, 49, 45, 11)
+    ju, ku = engine.jk(du)
+    je, ke = cjk.jk_entries(cjk.SRC_SYNTH, None, n, seed, du, ent)
+    for t, (p, q) in enumerate(ent):
+        assert abs(ju[p, q] - je[t]) <= TOL, (p, q)
+        assert abs(ku[0][p, q] - ke[0][t]) <= TOL and abs(ku[1][p, q] - ke[1][t]) <= TOL, (p, q)
+    assert np.abs(ju - ju.T).max() <= TOL and np.abs(ku - ku.transpose(0, 2, 1)).max() <= TOL
+    assert np.abs(ku[0] - ku[1]).max() > 1e-3   # the two spin planes really differ
     engine.attach_eri_synth(4, 1)   # release the 62 GB shard for the following tests

@@ -76,6 +76,34 @@ def test_mp2_n2_size(engine):
     assert abs(e - er) <= 1e-9
 
 
+def test_mp2_benzene_size_222(engine):
+    """configs[3] size: benzene def2-TZVP, N = 222, n_occ = 21 (n_occ * n_virt = 4221 -- the reference refuses it,
+    mp2.py:72).  The whole (ia|jb) tensor against the chunked-GEMM restatement of mp2.py:123-170 on the lazily
+    generated synthetic tensor, 64 sampled entries against the literal nesting of the four np.dot steps, E_corr
+    against the energy sum of mp2.py:240-254."""
+    from oracle import cjk
+    n, no, seed = 222, 21, 20261019
+    nv = n - no
+    c, eps = synth.synth_mo(n, no, seed)
+    engine.attach_eri_synth(n, seed)
+    e, iajb = engine.mp2_corr(c, eps, no, want_iajb=True)
+    er, ir = mp2_ref.mp2_corr_synth_chunked(n, seed, c, eps, no)
+    assert np.abs(iajb - ir).max() <= 1e-11, np.abs(iajb - ir).max()
+    # loop form (the reference's own nesting) on 2 occupied pairs x 32 virtual pairs, incl. i == j and a == b
+    rng = np.random.default_rng(5)
+    for i, j in ((3, 3), (20, 0)):
+        ab = [(0, 0), (nv - 1, nv - 1), (nv - 1, 0), (0, nv - 1)] + [tuple(int(v) for v in t) for t in rng.integers(0, nv, size=(28, 2))]
+        loop = cjk.mp2_entries_synth(n, seed, c, i, j, [(no + a, no + b) for a, b in ab])
+        got = np.array([iajb[i, a, j, b] for a, b in ab])
+        assert np.abs(got - loop).max() <= 1e-11, (i, j, np.abs(got - loop).max())
+    # |E_corr| of the synthetic tensor is ~7e3 Eh: the 1e-9 Eh gate is applied at the physical scale (orbital energies
+    # scaled so that |E_corr| ~ 1 Eh, same integrals); the unscaled sum must agree to 1e-12 relative
+    assert abs(e - er) <= 1e-12 * abs(er), (e, er)
+    scale = abs(er)
+    es = engine.mp2_corr(c, eps * scale, no)
+    assert abs(es - mp2_ref.energy_einsum(ir, eps[:no] * scale, eps[no:] * scale)) <= 1e-9
+
+
 def test_ao2mo_ijab(engine):
     """(ij|ab) block needed by CIS (cis_tdhf_tda_tddft.py:184-211)."""
     n, no, seed = 12, 4, 5

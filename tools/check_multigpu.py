@@ -48,6 +48,20 @@ for n, seed in ((70, 5), (37, 9), (130, 2)):
     e0 = et.clone()
     dist.broadcast(e0, 0)
     assert torch.equal(et, e0), f"SCF energies differ across ranks: {et.tolist()} vs {e0.tolist()}"
+    # the same two steps with the partials summed by NCCL between the two halves of the step (sqcc_scf_jk ->
+    # all-reduce -> sqcc_scf_finish): the Fock matrix must never be built from a rank's partial J/K
+    eng.set_exchange("nccl")
+    eng.scf_set_density(synth.synth_density_rhf(n, n // 4, 3))
+    f1 = eng.scf_fock_energy()
+    eng.scf_update()
+    f2 = eng.scf_fock_energy()
+    assert abs(f1 - e1) <= 1e-9 and abs(f2 - e2) <= 1e-9, (rank, e1, f1, e2, f2)
+    # ... and against the host-side energy of the oracle's J/K for the same density (hf_ksdft.py:498-499, :556-557)
+    d0 = synth.synth_density_rhf(n, n // 4, 3)
+    jr, kr = cjk.jk_packed(packed, n, d0)
+    e_ref = 0.5 * np.sum(d0 * (2.0 * h + jr - 0.5 * kr))
+    assert abs(e1 - e_ref) <= 1e-9 * max(1.0, abs(e_ref)), (e1, e_ref)
+    eng.set_exchange("p2p")
 assert worst <= TOL, worst
 eng.close()
 dist.barrier()
