@@ -20,10 +20,12 @@
  *
  * Packed ERI layouts (8-fold symmetry, i>=j, k>=l, ij>=kl, ij = i(i+1)/2+j):
  *   canonical : offset ij(ij+1)/2 + kl, plain (ij|kl).
- *   native v1 : same row order; inside row ij the sub-row of k (l = 0..k, or 0..j when k == i) is
- *               padded to a multiple of 16 doubles (128-byte aligned sub-rows, zero pad cells); the stored value
- *               is (ij|kl) * 0.5^[i==j] * 0.5^[k==l] * 0.5^[ij==kl].  A rank holds the contiguous
- *               row range [ij_begin, ij_end) ("pair-block shard").
+ *   native v2 : tile-interleaved (sqcc_b200/csrc/layout.cuh; restated in oracle/packing.py).  A tile ("pair-block")
+ *               is a 4 x 4 block of rows (i, j); inside a tile, for every sub-row k and 64-column chunk c, the 16 rows
+ *               lie side by side as one contiguous "piece" [16][w] (w = 64, or 16/32/48 on the triangular edge
+ *               l <= k), pieces ordered chunk-major; cells outside the canonical range are stored as 0.0.  The stored
+ *               value is (ij|kl) * 0.5^[i==j] * 0.5^[k==l] * 0.5^[ij==kl].  A rank holds a contiguous tile range
+ *               [t_begin, t_end) ("pair-block shard") = a contiguous byte range of the tensor.
  */
 #ifndef SQCC_B200_H
 #define SQCC_B200_H
@@ -56,28 +58,24 @@ int sqcc_ctx_synchronize(sqcc_ctx *ctx);
 /* ---- layout helpers (pure host arithmetic, usable without a GPU) --------------------------- */
 int64_t sqcc_npair(int n);
 int64_t sqcc_nquad(int n);
-/* Equal-area cut of the row range into `world` contiguous pair-block shards, row granularity. */
-int sqcc_shard_rows(int n, int world, int rank, int64_t *ij_begin, int64_t *ij_end);
-/* Tile-granular shards (the multi-GPU default).  A tile ("pair-block") is a 4 x 4 block of rows (i, j): i-blocks are
- * anchored at the top of the i range (the last block ends at i = N), j-blocks at multiples of 4; global tile order is
- * i-block ascending, j-block ascending.  A shard is a contiguous tile range [t_begin, t_end); inside the shard buffer
- * its rows are stored in pair-index order.  Cutting at tile boundaries keeps every 4 x 4 row-block of the J/K kernel
- * full on every rank (row-granular cuts leave half-empty blocks at the shard edges: -20 % at 8 ranks, N = 494). */
+/* Tile-granular shards.  A tile ("pair-block") is a 4 x 4 block of rows (i, j): i-blocks are anchored at the top of
+ * the i range (the last block ends at i = N), j-blocks at multiples of 4; global tile order is i-block ascending,
+ * j-block ascending.  A shard is a contiguous tile range [t_begin, t_end), cut for equal streaming
+ * cost; every 4 x 4 row-block of the J/K kernel is whole on exactly one rank. */
 int64_t sqcc_tile_count(int n);
 int sqcc_shard_tiles(int n, int world, int rank, int64_t *t_begin, int64_t *t_end);
 /* Rows held by the tile range: for every i the interval [jlo[i], jhi[i]) of j (arrays of N ints). */
 int sqcc_tile_rows(int n, int64_t t_begin, int64_t t_end, int *jlo, int *jhi);
+/* Length in doubles of the native-v2 shard holding tiles [t_begin, t_end). */
 int64_t sqcc_native_len_tiles(int n, int64_t t_begin, int64_t t_end);
-/* Length in doubles of the native-v1 shard holding rows [ij_begin, ij_end). */
-int64_t sqcc_native_len(int n, int64_t ij_begin, int64_t ij_end);
-/* Offset (doubles, relative to the shard start) of element (i,j,k,l) in native v1; -1 if not canonical. */
-int64_t sqcc_native_offset(int n, int64_t ij_begin, int i, int j, int k, int l);
+/* Offset (doubles, relative to the start of tile t_begin) of element (i,j,k,l) in native v2; -1 if not canonical or
+ * stored before t_begin. */
+int64_t sqcc_native_offset(int n, int64_t t_begin, int i, int j, int k, int l);
 
 /* ---- ERI ingest: replaces the consumption of interface_psi4.py:177-190 (full N^4 host tensor) ---- */
-/* Attach a caller-owned device buffer of sqcc_native_len(...) doubles as this rank's ERI shard and build
- * the tile schedule.  The buffer must stay alive until detach/destroy. */
-int sqcc_eri_attach(sqcc_ctx *ctx, double *d_native, int n, int64_t ij_begin, int64_t ij_end);
-/* Same for a tile-range shard: buffer of sqcc_native_len_tiles(...) doubles. */
+/* Attach a caller-owned device buffer of sqcc_native_len_tiles(...) doubles (16-byte aligned) as this rank's ERI shard
+ * and build the task schedule.  The buffer must stay alive until detach/destroy.  N <= 4096 (64-bit offsets
+ * throughout; what fits is bounded by HBM: N = 494 is 63.5 GB, N ~ 640 fills one 180 GB B200, N ~ 1080 eight). */
 int sqcc_eri_attach_tiles(sqcc_ctx *ctx, double *d_native, int n, int64_t t_begin, int64_t t_end);
 /* Fill the attached shard with the counter-based synthetic tensor (oracle/synth.py). */
 int sqcc_eri_synth(sqcc_ctx *ctx, uint64_t seed);
@@ -105,9 +103,17 @@ int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, doubl
 /* Same through host buffers (H2D of D, D2H of J/K inside; stream-synchronous).  Page-locked host buffers are copied
  * from / to directly; pageable ones go through the context's pinned staging area. */
 int sqcc_jk_build_host(sqcc_ctx *ctx, const double *h_D, int nspin, int want_k, double *h_J, double *h_K);
-/* Select the kernel: 0 = cp.async-pipelined warp-task kernel (default), 1 = simple atomics kernel (cross-check),
- * 2 = warp-task kernel with direct 128-bit global loads (no shared-memory ring), 16+c = tuning configuration c. */
+/* Select the kernel: 0 = streaming warp-task kernel, TMA ring (default), 1 = simple atomics kernel (cross-check),
+ * 16+c = streaming kernel, tuning configuration c (1: cp.async ring instead of TMA, 2: TMA + L2 prefetch). */
 int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant);
+/* Deterministic mode (on != 0): every flush of a partial sum into the J~/K~ work matrices is converted to 64-bit fixed
+ * point and added with an INTEGER atomic (associative), so J and K are bit-for-bit reproducible from run to run, under
+ * any task schedule, and -- with the fused exchange, which sums the ranks in a fixed order -- identical on all ranks.
+ * The scale is 2^s with (max |stored integral|) * max(sum |D2|, sum |Da|, sum |Db|) * 2^s < 2^59: resolution
+ * ~1e-15 relative to that bound (parity gate: 1e-11 absolute).  Ranks of a group must share one integral bound:
+ * sqcc_eri_absmax(ctx, &v, 0) reads this shard's, sqcc_eri_absmax(ctx, &v, 1) sets the agreed one (max over ranks). */
+int sqcc_jk_set_deterministic(sqcc_ctx *ctx, int on);
+int sqcc_eri_absmax(sqcc_ctx *ctx, double *absmax, int set);
 /* Tuning aid: enable != 0 makes every warp of the pipelined kernel record {start ns, end ns, tasks done}; h_out (optional,
  * [max_warps][3]) receives the trace of the last launch.  Returns the number of warps written. */
 int sqcc_jk_trace(sqcc_ctx *ctx, int enable, uint64_t *h_out, int max_warps);

@@ -6,10 +6,9 @@ canonical  (SURVEY.md A.1): pair index ``ij = i(i+1)/2 + j`` (i >= j), quads ``i
            ``ij(ij+1)/2 + kl``; holds the plain integral (ij|kl) as produced by
            ``interface_psi4.py:177-190`` (``ERI[i,j,k,l]``).
 
-native v1  (what the CUDA kernels stream): same rows ``ij`` in the same order; inside a row the
-           sub-row for ``k`` (l = 0..k, or l = 0..j when k == i) is padded to a multiple of 16
-           doubles so that every sub-row starts 128-byte aligned (one L1 line per 8-lane quarter of a 128-bit load).  Pad cells are 0.0.
-           Stored value is (ij|kl) * f with the degeneracy factor
+native v2  (what the CUDA kernels stream; sqcc_b200/csrc/layout.cuh): tile-interleaved.  The 16 rows of a 4 x 4 block
+           of rows (i, j) lie side by side for every (sub-row k, 64-column chunk) as one contiguous "piece"; cells
+           outside the canonical range are 0.0.  Stored value is (ij|kl) * f with the degeneracy factor
            f = 0.5^[i==j] * 0.5^[k==l] * 0.5^[ij==kl]   (exact powers of two).
 """
 import numpy as np
@@ -64,35 +63,91 @@ def unpack_canonical(packed, n):
     return np.ascontiguousarray(m[idx[:, :, None, None], idx[None, None, :, :]])
 
 
-# ---------------------------------------------------------------- native v1 layout
-LAYOUT_ALIGN = 16  # doubles; must equal SUBROW_ALIGN in sqcc_b200/csrc/common.cuh
+# ---------------------------------------------------------------- native v2 layout (sqcc_b200/csrc/layout.cuh)
+# Tile-interleaved: a tile is a 4 x 4 block of rows (i, j); i-blocks are anchored at the top of the i range (block ib
+# covers i in [ihi - 4, ihi), ihi = n - 4 (nb - 1 - ib)); j-blocks start at multiples of 4; tile order ib ascending, jb
+# ascending.  Inside a tile, chunk-major: for c: for k = 64 c .. imax: a "piece" [16][w] with w = min(64, 16 ((k - 64 c)
+# // 16 + 1)); row slot r = 4 (j % 4) + (i - (ihi - 4)).  Cells outside the canonical range hold 0.0.
+LAY_CHUNK = 64
+LAY_ROWS = 16
 
 
-def pad_sub(x):
-    return (x + (LAYOUT_ALIGN - 1)) // LAYOUT_ALIGN * LAYOUT_ALIGN
+def lay_nblocks(n):
+    return (n + 3) // 4
 
 
-def subrow_offset(k):
-    """Te(k) = sum_{k' < k} pad_sub(k' + 1) = A (M + 1) (A M / 2 + r), A = LAYOUT_ALIGN, M = k // A, r = k % A."""
-    k = np.asarray(k, dtype=np.int64)
-    m, r = k // LAYOUT_ALIGN, k % LAYOUT_ALIGN
-    return LAYOUT_ALIGN * (m + 1) * ((LAYOUT_ALIGN // 2) * m + r)
+def lay_ihi(n, ib):
+    return n - 4 * (lay_nblocks(n) - 1 - ib)
 
 
-def row_length(i, j):
-    """Padded length (doubles) of row (i, j): sub-rows k < i are full, sub-row k == i holds l <= j."""
-    return subrow_offset(i) + pad_sub(np.asarray(j, dtype=np.int64) + 1)
+def lay_iblock(n, i):
+    return lay_nblocks(n) - 1 - (n - 1 - i) // 4
 
 
-def row_offsets(n, ij_begin=0, ij_end=None):
-    """int64[npair_local + 1] offsets (doubles) of rows ij_begin..ij_end-1 relative to the shard start."""
-    if ij_end is None:
-        ij_end = npair(n)
-    I, J = pair_unrank(n)
-    lens = row_length(I[ij_begin:ij_end], J[ij_begin:ij_end])
-    out = np.zeros(ij_end - ij_begin + 1, dtype=np.int64)
-    np.cumsum(lens, out=out[1:])
-    return out
+def lay_njb(imax):
+    return imax // 4 + 1
+
+
+def lay_w(m):
+    return 64 if m >= 48 else 16 * (m // 16 + 1)
+
+
+def lay_S(m):
+    """sum of lay_w(m') for m' < m."""
+    if m >= 48:
+        return 64 * (m - 24)
+    q, r = m // 16, m % 16
+    return 16 * (q + 1) * (8 * q + r)
+
+
+def lay_piece_offset(imax, c, k):
+    return LAY_ROWS * (64 * (c * (imax - 23) - 32 * c * (c - 1)) + lay_S(k - LAY_CHUNK * c))
+
+
+def lay_tile_len(imax):
+    return lay_piece_offset(imax, imax // 64, imax + 1)
+
+
+def tile_tables(n):
+    """(ibase, tfirst): offset (doubles) and tile index of the first tile of every i-block, length nb + 1."""
+    nb = lay_nblocks(n)
+    ibase, tfirst = [0], [0]
+    for ib in range(nb):
+        imax = lay_ihi(n, ib) - 1
+        ibase.append(ibase[-1] + lay_njb(imax) * lay_tile_len(imax))
+        tfirst.append(tfirst[-1] + lay_njb(imax))
+    return ibase, tfirst
+
+
+def tile_count(n):
+    return tile_tables(n)[1][-1]
+
+
+def tile_offset(n, t):
+    ibase, tfirst = tile_tables(n)
+    nb = lay_nblocks(n)
+    if t >= tfirst[nb]:
+        return ibase[nb]
+    ib = max(b for b in range(nb) if tfirst[b] <= t)
+    return ibase[ib] + (t - tfirst[ib]) * lay_tile_len(lay_ihi(n, ib) - 1)
+
+
+def native_len(n, t_begin=0, t_end=None):
+    if t_end is None:
+        t_end = tile_count(n)
+    return tile_offset(n, t_end) - tile_offset(n, t_begin)
+
+
+def native_offset(n, i, j, k, l):
+    """Offset (doubles, from the start of the full tensor) of the canonical element (i, j, k, l)."""
+    ibase, _ = tile_tables(n)
+    ib = lay_iblock(n, i)
+    ihi = lay_ihi(n, ib)
+    imax = ihi - 1
+    c = l // 64
+    m = k - 64 * c
+    slot = 4 * (j % 4) + (i - (ihi - 4))
+    return ibase[ib] + (j // 4) * lay_tile_len(imax) + lay_piece_offset(imax, c, k) + slot * lay_w(m) + (l - 64 * c)
 
 
 def degeneracy_factor(i, j, k, l):
@@ -100,21 +155,40 @@ def degeneracy_factor(i, j, k, l):
     return f * np.where((i == k) & (j == l), 0.5, 1.0)
 
 
-def canonical_to_native(packed, n, ij_begin=0, ij_end=None):
-    """Canonical packed vector -> native v1 shard (rows ij_begin..ij_end-1)."""
-    if ij_end is None:
-        ij_end = npair(n)
-    I, J = pair_unrank(n)
-    ro = row_offsets(n, ij_begin, ij_end)
-    out = np.zeros(ro[-1])
-    K, L = I, J  # same unranking for kl
-    te = subrow_offset(K)
-    for ij in range(ij_begin, ij_end):
-        i, j = int(I[ij]), int(J[ij])
-        kl = np.arange(ij + 1)
-        k, l = K[kl], L[kl]
-        v = packed[canonical_offset(ij, kl)] * degeneracy_factor(i, j, k, l)
-        out[ro[ij - ij_begin] + te[kl] + l] = v
+def canonical_to_native(packed, n, t_begin=0, t_end=None):
+    """Canonical packed vector -> native v2 shard holding the tiles [t_begin, t_end)."""
+    ibase, tfirst = tile_tables(n)
+    if t_end is None:
+        t_end = tfirst[-1]
+    base = tile_offset(n, t_begin)
+    out = np.zeros(tile_offset(n, t_end) - base)
+    for ib in range(lay_nblocks(n)):
+        ihi = lay_ihi(n, ib)
+        imax = ihi - 1
+        tl = lay_tile_len(imax)
+        for jb in range(lay_njb(imax)):
+            t = tfirst[ib] + jb
+            if t < t_begin or t >= t_end:
+                continue
+            tile = ibase[ib] + jb * tl - base
+            for a in range(4):
+                i = ihi - 4 + a
+                if i < 0:
+                    continue
+                for b in range(4):
+                    j = 4 * jb + b
+                    if j > i:
+                        continue
+                    ij = pair_index(i, j)
+                    for k in range(i + 1):
+                        lmax = k if k < i else j
+                        l = np.arange(lmax + 1)
+                        v = packed[canonical_offset(ij, pair_index(k, l))] * degeneracy_factor(i, j, k, l)
+                        c = l // 64
+                        m = k - 64 * c
+                        w = np.where(m >= 48, 64, 16 * (m // 16 + 1))
+                        po = np.array([lay_piece_offset(imax, int(cc), k) for cc in range(int(c.max()) + 1)])
+                        out[tile + po[c] + (4 * b + a) * w + (l - 64 * c)] = v
     return out
 
 
@@ -122,34 +196,10 @@ def native_to_canonical(native, n):
     """Inverse of canonical_to_native for a full (unsharded) tensor."""
     p = npair(n)
     I, J = pair_unrank(n)
-    ro = row_offsets(n)
     out = np.zeros(nquad(n))
-    te = subrow_offset(I)
     for ij in range(p):
         i, j = int(I[ij]), int(J[ij])
-        kl = np.arange(ij + 1)
-        k, l = I[kl], J[kl]
-        out[canonical_offset(ij, kl)] = native[ro[ij] + te[kl] + l] / degeneracy_factor(i, j, k, l)
+        for kl in range(ij + 1):
+            k, l = int(I[kl]), int(J[kl])
+            out[canonical_offset(ij, kl)] = native[native_offset(n, i, j, k, l)] / float(degeneracy_factor(i, j, k, l))
     return out
-
-
-def shard_row_cuts(n, world, align=1):
-    """Equal-AREA cuts of the row range [0, npair) into `world` contiguous shards.
-
-    Returns int64[world + 1] pair-index boundaries.  `align` rounds interior cuts to i-block boundaries:
-    a cut is always placed at a row with j == 0 and i % align == 0 so kernels can tile rows by i-block.
-    """
-    I, J = pair_unrank(n)
-    ro = row_offsets(n)
-    total = ro[-1]
-    cuts = [0]
-    # candidate cut rows: start of i-blocks
-    cand_i = np.arange(0, n, align, dtype=np.int64)
-    cand_ij = cand_i * (cand_i + 1) // 2
-    cand_off = ro[cand_ij]
-    for g in range(1, world):
-        target = total * g / world
-        c = int(np.argmin(np.abs(cand_off - target)))
-        cuts.append(int(max(cand_ij[c], cuts[-1])))
-    cuts.append(npair(n))
-    return np.asarray(cuts, dtype=np.int64)

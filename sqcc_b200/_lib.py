@@ -20,14 +20,11 @@ SIGNATURES = {
     "sqcc_ctx_synchronize": (c_int, [c_void_p]),
     "sqcc_npair": (c_i64, [c_int]),
     "sqcc_nquad": (c_i64, [c_int]),
-    "sqcc_shard_rows": (c_int, [c_int, c_int, c_int, c_i64_p, c_i64_p]),
     "sqcc_tile_count": (c_i64, [c_int]),
     "sqcc_shard_tiles": (c_int, [c_int, c_int, c_int, c_i64_p, c_i64_p]),
     "sqcc_tile_rows": (c_int, [c_int, c_i64, c_i64, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "sqcc_native_len_tiles": (c_i64, [c_int, c_i64, c_i64]),
-    "sqcc_native_len": (c_i64, [c_int, c_i64, c_i64]),
     "sqcc_native_offset": (c_i64, [c_int, c_i64, c_int, c_int, c_int, c_int]),
-    "sqcc_eri_attach": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_i64]),
     "sqcc_eri_attach_tiles": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_i64]),
     "sqcc_eri_synth": (c_int, [c_void_p, c_u64]),
     "sqcc_eri_pack_full_slab": (c_int, [c_void_p, c_void_p, c_int, c_int]),
@@ -39,6 +36,8 @@ SIGNATURES = {
     "sqcc_jk_build": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sqcc_jk_build_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sqcc_jk_set_variant": (c_int, [c_void_p, c_int]),
+    "sqcc_jk_set_deterministic": (c_int, [c_void_p, c_int]),
+    "sqcc_eri_absmax": (c_int, [c_void_p, c_double_p, c_int]),
     "sqcc_comm_export": (c_int, [c_void_p, c_void_p]),
     "sqcc_comm_attach": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "sqcc_comm_attach_local": (c_int, [ctypes.POINTER(c_void_p), c_int]),

@@ -140,7 +140,9 @@ class FockEngine:
         self._detach_peers()
         self.n = int(n)
         self.plan = ShardPlan(n, self.world, self.rank)
-        self.eri = torch.empty(max(self.plan.native_len, 2), dtype=torch.float64, device=self.device)
+        # + 4 KB of slack: the zero-fill cp.async of the lanes past a narrow piece carry (unread) addresses up to 368
+        # bytes beyond the last piece
+        self.eri = torch.empty(self.plan.native_len + 512, dtype=torch.float64, device=self.device)
         self._use_stream()
         _lib.check(self.lib.sqcc_eri_attach_tiles(self.ctx, _ptr(self.eri), self.n, self.plan.t_begin, self.plan.t_end))
         self._p2p = False
@@ -265,6 +267,19 @@ class FockEngine:
 
     def set_jk_variant(self, variant):
         _lib.check(self.lib.sqcc_jk_set_variant(self.ctx, int(variant)))
+
+    def set_deterministic(self, on=True):
+        """Deterministic J/K (include/sqcc_b200.h: sqcc_jk_set_deterministic): fixed-point integer accumulation, results
+        bit-for-bit reproducible from run to run and identical on every rank of a peer group.  With several ranks the
+        bound on the stored integrals is agreed once (max over the shards); call again after attaching a new tensor."""
+        _lib.check(self.lib.sqcc_jk_set_deterministic(self.ctx, int(bool(on))))
+        self._deterministic = bool(on)
+        if on and self._group_size() > 1 and self.eri is not None:
+            import torch.distributed as dist
+            m = torch.tensor([float(self.eri.abs().max().item())], dtype=torch.float64, device=self.device)
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+            v = ctypes.c_double(float(m.item()))
+            _lib.check(self.lib.sqcc_eri_absmax(self.ctx, ctypes.byref(v), 1))
 
     # ------------------------------------------------------------------ J/K
     def jk_device(self, d, want_k=True, out=None):

@@ -51,36 +51,9 @@ int timer_stop(sqcc_ctx *ctx, int slot)
     return SQCC_OK;
 }
 
-// Offset (doubles) of row ij = (i, j) from the start of the full native tensor.
-static int64_t global_row_offset(int64_t ij)
-{
-    int i, j;
-    int64_t t = (int64_t)((sqrt(8.0 * (double)ij + 1.0) - 1.0) * 0.5);
-    while (t * (t + 1) / 2 > ij) --t;
-    while ((t + 1) * (t + 2) / 2 <= ij) ++t;
-    i = (int)t;
-    j = (int)(ij - t * (t + 1) / 2);
-    return iblock_offset(i) + (int64_t)j * subrow_offset(i) + subrow_offset(j);
-}
-
-// Row index at which shard g of `world` starts: equal-area cut with row granularity.
-static int64_t shard_cut(int n, int world, int g)
-{
-    const int64_t np_ = (int64_t)n * (n + 1) / 2;
-    if (g <= 0) return 0;
-    if (g >= world) return np_;
-    const double target = (double)global_row_offset(np_) * (double)g / (double)world;
-    int64_t lo = 0, hi = np_;
-    while (lo < hi) {  // first row whose start offset >= target
-        int64_t mid = (lo + hi) / 2;
-        if ((double)global_row_offset(mid) < target) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// Tile index at which shard g of `world` starts: equal-COST cut with 4 x 4 tile granularity.  The cost of a row is its
-// native length times (1 + alpha / (i + 1)): short rows spend relatively more warp tasks on the triangular edge
-// (l <= k masking) of the sub-rows, measured as ~8 % lower streaming rate for the i < 294 shard of N = 494 (alpha = 40).
+// Tile index at which shard g of `world` starts: equal-COST cut with 4 x 4 tile granularity.  The cost of a tile is its
+// native length times (1 + alpha / (imax + 1)): short rows spend relatively more of their sub-rows on the triangular edge
+// (narrow pieces move fewer bytes per kernel iteration).
 static double shard_alpha()
 {
     if (const char *e = getenv("SQCC_SHARD_ALPHA")) return atof(e);
@@ -92,21 +65,15 @@ static int64_t tile_cut(int n, int world, int g)
     const int64_t nt = tile_count(n);
     if (g <= 0) return 0;
     if (g >= world) return nt;
-    // cumulative native length by tile (tile order: i-block ascending, j-block ascending)
+    // cumulative cost by tile (tile order: i-block ascending, j-block ascending)
     std::vector<double> cum;
     cum.reserve(nt + 1);
     cum.push_back(0.0);
     const double alpha = shard_alpha();
-    const int nb = (n + 3) / 4;
-    for (int b = 0; b < nb; ++b) {
-        int lo = n - 4 * (nb - b), hi = lo + 4;
-        if (lo < 0) lo = 0;
-        for (int j0 = 0; j0 <= hi - 1; j0 += 4) {
-            double cost = 0.0;
-            for (int i = lo; i < hi; ++i)
-                for (int j = j0; j < j0 + 4 && j <= i; ++j) cost += (double)row_length(i, j) * (1.0 + alpha / (i + 1.0));
-            cum.push_back(cum.back() + cost);
-        }
+    for (int ib = 0; ib < lay_nblocks(n); ++ib) {
+        const int imax = lay_ihi(n, ib) - 1;
+        const double cost = (double)lay_tile_len(imax) * (1.0 + alpha / (imax + 1.0));
+        for (int jb = 0; jb < lay_njb(imax); ++jb) cum.push_back(cum.back() + cost);
     }
     const double target = cum.back() * (double)g / (double)world;
     int64_t lo = 0, hi = nt;
@@ -166,9 +133,7 @@ int sqcc_ctx_destroy(sqcc_ctx *ctx)
 {
     if (!ctx) return SQCC_OK;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_rowoff);
-    cudaFree(ctx->d_ioff);
-    cudaFree(ctx->d_jlo);
+    cudaFree(ctx->d_ibase);
     for (auto &sc : ctx->sched) {
         cudaFree(sc.d_rowblocks);
         cudaFree(sc.d_tasks);
@@ -212,16 +177,6 @@ int64_t sqcc_nquad(int n)
     return p * (p + 1) / 2;
 }
 
-int sqcc_shard_rows(int n, int world, int rank, int64_t *ij_begin, int64_t *ij_end)
-{
-    SQCC_REQUIRE(n > 0 && world > 0 && rank >= 0 && rank < world && ij_begin && ij_end, "bad shard arguments");
-    int64_t a = shard_cut(n, world, rank), b = shard_cut(n, world, rank + 1);
-    if (b < a) b = a;
-    *ij_begin = a;
-    *ij_end = b;
-    return SQCC_OK;
-}
-
 int64_t sqcc_tile_count(int n) { return n > 0 ? tile_count(n) : -1; }
 
 int sqcc_shard_tiles(int n, int world, int rank, int64_t *t_begin, int64_t *t_end)
@@ -249,48 +204,34 @@ int sqcc_tile_rows(int n, int64_t t_begin, int64_t t_end, int *jlo, int *jhi)
 int64_t sqcc_native_len_tiles(int n, int64_t t_begin, int64_t t_end)
 {
     if (n <= 0 || t_begin < 0 || t_end < t_begin || t_end > tile_count(n)) return -1;
-    std::vector<int> a, b;
-    tile_intervals(n, t_begin, t_end, a, b);
-    return intervals_native_len(n, a, b);
+    return tile_offset(n, t_end) - tile_offset(n, t_begin);
 }
 
-int64_t sqcc_native_len(int n, int64_t ij_begin, int64_t ij_end)
+int64_t sqcc_native_offset(int n, int64_t t_begin, int i, int j, int k, int l)
 {
-    if (n <= 0 || ij_begin < 0 || ij_end < ij_begin || ij_end > sqcc_npair(n)) return -1;
-    return global_row_offset(ij_end) - global_row_offset(ij_begin);
-}
-
-int64_t sqcc_native_offset(int n, int64_t ij_begin, int i, int j, int k, int l)
-{
-    if (i < 0 || i >= n || j < 0 || j > i || k < 0 || l < 0 || l > k) return -1;
-    if (pair_index(k, l) > pair_index(i, j) || pair_index(i, j) < ij_begin) return -1;
-    return global_row_offset(pair_index(i, j)) - global_row_offset(ij_begin) + subrow_offset(k) + l;
-}
-
-int sqcc_eri_attach(sqcc_ctx *ctx, double *d_native, int n, int64_t ij_begin, int64_t ij_end)
-{
-    SQCC_REQUIRE(ctx && d_native, "null ctx / buffer");
-    // the J/K kernel keeps 32-bit byte offsets between the rows of a 4x4 row-block: 12 i^3 bytes < 2^32
-    SQCC_REQUIRE(n > 0 && n <= 680, "N out of range (1..680: 32-bit row offsets inside a row-block)");
-    SQCC_REQUIRE(ij_begin >= 0 && ij_end >= ij_begin && ij_end <= sqcc_npair(n), "bad row range");
-    row_intervals(n, ij_begin, ij_end, ctx->jlo, ctx->jhi);
-    return attach_common(ctx, d_native, n);
+    if (n <= 0 || i < 0 || i >= n || j < 0 || j > i || k < 0 || l < 0 || l > k) return -1;
+    if (pair_index(k, l) > pair_index(i, j)) return -1;
+    std::vector<int64_t> ibase, tfirst;
+    tile_tables(n, ibase, tfirst);
+    if (tfirst[lay_iblock(n, i)] + (j >> 2) < t_begin) return -1;
+    return lay_offset(ibase.data(), n, i, j, k, l) - tile_offset(n, t_begin);
 }
 
 int sqcc_eri_attach_tiles(sqcc_ctx *ctx, double *d_native, int n, int64_t t_begin, int64_t t_end)
 {
     SQCC_REQUIRE(ctx && d_native, "null ctx / buffer");
-    SQCC_REQUIRE(n > 0 && n <= 680, "N out of range (1..680: 32-bit row offsets inside a row-block)");
+    SQCC_REQUIRE(n > 0 && n <= 4096, "N out of range (1..4096)");
     SQCC_REQUIRE(t_begin >= 0 && t_end >= t_begin && t_end <= tile_count(n), "bad tile range");
-    tile_intervals(n, t_begin, t_end, ctx->jlo, ctx->jhi);
+    ctx->t_begin = t_begin;
+    ctx->t_end = t_end;
     return attach_common(ctx, d_native, n);
 }
 
 int sqcc_eri_synth(sqcc_ctx *ctx, uint64_t seed)
 {
     SQCC_REQUIRE(ctx && ctx->d_eri, "no ERI attached");
-    SQCC_CUDA(cudaMemsetAsync(ctx->d_eri, 0, sizeof(double) * ctx->native_len, ctx->stream));
-    return eri_synth(ctx, seed);
+    ctx->eri_absmax = -1.0;
+    return eri_synth(ctx, seed);   // writes every cell of the shard (zeros outside the canonical range)
 }
 
 int sqcc_eri_pack_full_slab(sqcc_ctx *ctx, const double *d_slab, int p0, int np)
@@ -359,10 +300,29 @@ int sqcc_eri_unpack_full(sqcc_ctx *ctx, double *d_eri_full)
 
 int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant)
 {
-    SQCC_REQUIRE(ctx && variant >= 0 && (variant <= 2 || (variant >= 16 && variant <= 23)),
-                 "variant must be 0 (pipelined), 1 (simple), 2 (direct-load) or 16+cfg (pipelined, tuning cfg)");
+    SQCC_REQUIRE(ctx && variant >= 0 && (variant <= 1 || (variant >= 16 && variant <= 23)),
+                 "variant must be 0 (streaming kernel), 1 (simple atomics kernel) or 16+cfg (streaming kernel, tuning cfg)");
     ctx->jk_variant = variant < 16 ? variant : 0;
     ctx->jk_cfg = variant >= 16 ? variant - 16 : 0;
+    return SQCC_OK;
+}
+
+int sqcc_jk_set_deterministic(sqcc_ctx *ctx, int on)
+{
+    SQCC_REQUIRE(ctx, "null ctx");
+    ctx->jk_fixed = on != 0;
+    return SQCC_OK;
+}
+
+int sqcc_eri_absmax(sqcc_ctx *ctx, double *absmax, int set)
+{
+    SQCC_REQUIRE(ctx && absmax, "null ctx / value");
+    if (set) {
+        SQCC_REQUIRE(*absmax >= 0.0, "negative bound");
+        ctx->eri_absmax = *absmax;
+    } else {
+        *absmax = ctx->eri_absmax;
+    }
     return SQCC_OK;
 }
 

@@ -90,8 +90,10 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned 
 }
 
 // grid = (CTAs per rank, ranks emulated by this launch); cooperative launch (CTA 0 of a rank waits for its siblings).
+// inv_scale != 0: the accumulators are 64-bit fixed point (deterministic mode): integer sums, converted in phase 2.
 __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, int world, int nspin, int want_k, int n,
-                                                        int ldd, unsigned long long epoch, unsigned int bar_target)
+                                                        int ldd, unsigned long long epoch, unsigned int bar_target,
+                                                        double inv_scale)
 {
     const CommRank &cr = views[blockIdx.y];
     const int me = cr.rank;
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
         const size_t s0 = total2 * (size_t)me / world, s1 = total2 * (size_t)(me + 1) / world;
         for (size_t t = s0 + (size_t)blockIdx.x * blockDim.x + tid; t < s1; t += (size_t)gridDim.x * blockDim.x) {
             double2 sum = make_double2(0.0, 0.0);
+            long long ix = 0, iy = 0;
             for (int g0 = 0; g0 < world; g0 += 8) {   // eight peer loads in flight, summed in rank order
                 double2 v[8];
 #pragma unroll
@@ -129,8 +132,11 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
                 for (int u = 0; u < 8; ++u) {
                     sum.x += v[u].x;
                     sum.y += v[u].y;
+                    ix += __double_as_longlong(v[u].x);   // (zero bits are integer zero as well)
+                    iy += __double_as_longlong(v[u].y);
                 }
             }
+            if (inv_scale != 0.0) sum = make_double2(__longlong_as_double(ix), __longlong_as_double(iy));
 #pragma unroll 8
             for (int g = 0; g < world; ++g) st_peer2(cr.res[g] + 2 * t, sum);
         }
@@ -181,12 +187,23 @@ __global__ void __launch_bounds__(256) jk_reduce_kernel(const CommRank *views, i
                 if (idx < nn) {
                     const int pr = (int)(idx / n), q = (int)(idx % n);
                     const int hi = pr >= q ? pr : q, lo = pr >= q ? q : pr;
-                    const double jt = __ldcg(res + (size_t)hi * ldd + lo);
-                    jv[u] = pr == q ? 2.0 * jt : jt;
-                    if (want_k) {
-                        ka[u] = __ldcg(res + nl + (size_t)pr * ldd + q) + __ldcg(res + nl + (size_t)q * ldd + pr);
-                        if (nspin == 2)
-                            kb[u] = __ldcg(res + 2 * nl + (size_t)pr * ldd + q) + __ldcg(res + 2 * nl + (size_t)q * ldd + pr);
+                    if (inv_scale != 0.0) {
+                        const long long *ri = reinterpret_cast<const long long *>(res);
+                        const long long jt = __ldcg(ri + (size_t)hi * ldd + lo);
+                        jv[u] = (double)(pr == q ? 2 * jt : jt) * inv_scale;
+                        if (want_k) {
+                            ka[u] = (double)(__ldcg(ri + nl + (size_t)pr * ldd + q) + __ldcg(ri + nl + (size_t)q * ldd + pr)) * inv_scale;
+                            if (nspin == 2)
+                                kb[u] = (double)(__ldcg(ri + 2 * nl + (size_t)pr * ldd + q) + __ldcg(ri + 2 * nl + (size_t)q * ldd + pr)) * inv_scale;
+                        }
+                    } else {
+                        const double jt = __ldcg(res + (size_t)hi * ldd + lo);
+                        jv[u] = pr == q ? 2.0 * jt : jt;
+                        if (want_k) {
+                            ka[u] = __ldcg(res + nl + (size_t)pr * ldd + q) + __ldcg(res + nl + (size_t)q * ldd + pr);
+                            if (nspin == 2)
+                                kb[u] = __ldcg(res + 2 * nl + (size_t)pr * ldd + q) + __ldcg(res + 2 * nl + (size_t)q * ldd + pr);
+                        }
                     }
                 }
             }
@@ -287,7 +304,8 @@ static int launch_reduce(sqcc_ctx *ctx, const CommRank *d_views, int ranks_here,
                          unsigned long long epoch, unsigned int bar_target)
 {
     int world = ctx->comm.world, n = ctx->n, ldd = ctx->ldd;
-    void *args[] = {(void *)&d_views, &world, &nspin, &want_k, &n, &ldd, &epoch, &bar_target};
+    double inv_scale = ctx->fx_scale != 0.0 ? 1.0 / ctx->fx_scale : 0.0;
+    void *args[] = {(void *)&d_views, &world, &nspin, &want_k, &n, &ldd, &epoch, &bar_target, &inv_scale};
     SQCC_CUDA(cudaLaunchCooperativeKernel((const void *)jk_reduce_kernel, dim3(gx, ranks_here), dim3(256), args, 0,
                                           ctx->stream));
     ctx->launches++;

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/sqcc_b200.h"
+#include "layout.cuh"
 
 namespace sqcc {
 
@@ -33,42 +34,17 @@ void set_error(const std::string &msg);
         if (s_ != SQCC_OK) return s_;                                                                \
     } while (0)
 
-// ---------------------------------------------------------------- native v1 layout arithmetic
+// ---------------------------------------------------------------- packed layout arithmetic (native v2: layout.cuh)
 __host__ __device__ __forceinline__ int64_t pair_index(int64_t i, int64_t j) { return i * (i + 1) / 2 + j; }
-// Every sub-row is padded to a multiple of SUBROW_ALIGN doubles (128 bytes): a warp's 512-byte piece of a
-// sub-row then starts on a 128-byte line, so each 8-lane quarter of a 128-bit LDGSTS/LDG hits exactly one L1
-// line (4 shared-memory fill wavefronts and 16 L2 sectors per request instead of ~10 and ~20 when sub-rows are
-// only 16-byte aligned; measured with ncu, profiles/).
-constexpr int SUBROW_ALIGN = 16;
-__host__ __device__ __forceinline__ int64_t pad_sub(int64_t x) { return (x + (SUBROW_ALIGN - 1)) & ~(int64_t)(SUBROW_ALIGN - 1); }
-// Te(k) = sum_{k' < k} pad_sub(k' + 1) = A (M + 1) (A M / 2 + r),  A = SUBROW_ALIGN, M = k / A, r = k % A.
-__host__ __device__ __forceinline__ int64_t subrow_offset(int64_t k)
-{
-    const int64_t M = k / SUBROW_ALIGN, r = k % SUBROW_ALIGN;
-    return SUBROW_ALIGN * (M + 1) * ((SUBROW_ALIGN / 2) * M + r);
-}
-__host__ __device__ __forceinline__ int64_t row_length(int64_t i, int64_t j) { return subrow_offset(i) + pad_sub(j + 1); }
-// Offset of row (i, 0) from the start of the full tensor: sum over i' < i of [(i'+1) Te(i') + Te(i'+1)].
-int64_t iblock_offset(int64_t i);   // host, O(i) loop (cached table in the context for device use)
-__host__ __device__ __forceinline__ double degeneracy(int i, int j, int k, int l)
-{
-    double f = 1.0;
-    if (i == j) f *= 0.5;
-    if (k == l) f *= 0.5;
-    if (i == k && j == l) f *= 0.5;
-    return f;
-}
 
 // ---------------------------------------------------------------- J/K tile schedule
 constexpr int JK_KN = 16;      // k-range per warp task
-constexpr int JK_CHUNK = 64;   // l-chunk per warp task (2 per lane, one 128-bit load)
-constexpr int JK_NI = 4;       // rows i per row-block
-constexpr int JK_NJ = 2;       // rows j per row-block
+constexpr int JK_CHUNK = 64;   // l-chunk per warp task (2 per lane, one 128-bit load) == LAY_CHUNK
 
-struct RowBlock {
-    int i0, j0;
-    unsigned int mask;   // bit a*NJ+b: row (i0+a, j0+b) is held by this shard
-    int pad;
+struct RowBlock {        // 4 rows i x NB rows j of one tile
+    int64_t base;        // offset (doubles, shard-relative) of the tile
+    int imax;            // last i of the tile's i-block (rows i = imax-3 .. imax)
+    int j0;              // first j (4 jb, or 4 jb + 2 for the second 4 x 2 half)
 };
 struct JKTask {
     int k0;        // first k of the range (multiple of JK_KN)
@@ -77,7 +53,7 @@ struct JKTask {
     int rb_count;
 };
 struct JKSchedule {
-    int ni = 0, nj = 0;
+    int nb = 0;          // rows j per row-block (4 or 2)
     std::vector<RowBlock> h_rowblocks;
     std::vector<JKTask> h_tasks;
     RowBlock *d_rowblocks = nullptr;
@@ -121,27 +97,26 @@ struct sqcc_ctx {
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
 
-    // ERI shard (caller-owned).  A shard holds, for every i, the rows (i, j) with j in [jlo[i], jhi[i]) -- stored in
-    // pair-index order.  Row-range shards [ij_begin, ij_end) and tile-range shards (sqcc_shard_tiles) are both
-    // expressed this way.
+    // ERI shard (caller-owned): the contiguous tile range [t_begin, t_end) of the native v2 tensor (layout.cuh).
     double *d_eri = nullptr;
     int n = 0;
     int ldd = 0;  // padded leading dimension of the D/J~/K~ work matrices (multiple of 4)
-    std::vector<int> jlo, jhi;   // [n] held j interval per i (empty: jlo == jhi)
-    std::vector<int64_t> h_rowptr;  // [n + 1] number of held rows with i' < i
-    std::vector<int64_t> h_ioff;    // [n] local offset such that row (i,j) starts at h_ioff[i] + j Te(i) + Te(j)
+    int64_t t_begin = 0, t_end = 0;
+    int64_t shard_base = 0;      // offset (doubles) of tile t_begin in the full tensor
+    std::vector<int64_t> h_ibase, h_tfirst;   // [nb + 1] offset / tile index of the first tile of every i-block
+    int64_t *d_ibase = nullptr, *d_tfirst = nullptr;   // device copies (one allocation)
+    std::vector<int> jlo, jhi;   // [n] rows held: for every i the interval of j (host-side description of the shard)
     int64_t nrows = 0;           // held rows
-    bool whole = false;          // every row of the tensor is held (unsharded)
+    bool whole = false;          // every tile of the tensor is held (unsharded)
     int i_begin = 0, i_end = 0;  // i range with held rows
     int64_t native_len = 0;
     int64_t n_unique = 0;
-    int64_t *d_rowoff = nullptr;  // [nrows + 1] offsets of the held rows relative to the shard start
-    int64_t *d_rowij = nullptr;   // [nrows] global pair index of the held rows
-    int64_t *d_ioff = nullptr;    // [n] device copy of h_ioff
-    int *d_jlo = nullptr, *d_jhi = nullptr;   // [n] device copies of jlo / jhi (one allocation)
-    sqcc::JKSchedule sched[3];    // row-block shapes [0]: 4x2 (RHF, J-only)  [1]: 2x2 (UHF)  [2]: 4x4 (tuning)
+    double eri_absmax = -1.0;    // max |stored value| (lazily computed: deterministic fixed-point mode)
+    sqcc::JKSchedule sched[2];    // row-block shapes [0]: 4x4 (RHF, J-only)  [1]: 4x2 (UHF)
     int jk_variant = 0;
-    int jk_cfg = 0;  // tuning knob of the pipelined kernel (warps, stages), see launch_pipe
+    int jk_cfg = 0;  // tuning knob of the streaming kernel, see jk_partial
+    int jk_fixed = 0;  // deterministic mode: 64-bit fixed-point accumulation (sqcc_jk_set_deterministic)
+    double fx_scale = 0.0;   // fixed-point scale of the accumulators of the last build (0: floating point)
 
     // J/K scratch
     double *d_dwork = nullptr;   // [3][N][ldd]: D2 = 2*(Da+Db), Da, Db (padded)
@@ -183,9 +158,9 @@ int timer_stop(sqcc_ctx *ctx, int slot);
 // eri_layout.cu
 void pair_unrank_host(int64_t ij, int &i, int &j);
 int64_t tile_count(int n);
+void tile_tables(int n, std::vector<int64_t> &ibase, std::vector<int64_t> &tfirst);
+int64_t tile_offset(int n, int64_t t);
 int tile_intervals(int n, int64_t t_begin, int64_t t_end, std::vector<int> &jlo, std::vector<int> &jhi);
-int row_intervals(int n, int64_t ij_begin, int64_t ij_end, std::vector<int> &jlo, std::vector<int> &jhi);
-int64_t intervals_native_len(int n, const std::vector<int> &jlo, const std::vector<int> &jhi);
 int eri_build_tables(sqcc_ctx *ctx);
 int eri_synth(sqcc_ctx *ctx, uint64_t seed);
 int eri_pack_full_slab(sqcc_ctx *ctx, const double *d_slab, int p0, int np);

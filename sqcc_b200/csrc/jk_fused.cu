@@ -1,4 +1,4 @@
-// Fused Coulomb/exchange build over the native-v1 packed ERI shard (one pass, FP64).
+// Fused Coulomb/exchange build over the native v2 packed ERI shard (one pass, FP64).
 //
 // Replaces the loop nests hf_ksdft.py:483-487 (J), :491-495 (K), and the UHF/UKS variants :510-515,
 // :522-526, :531-535.  For every stored v = (ij|kl) * f  (SURVEY.md A.1, D symmetric, D2 = 2*(Da+Db)):
@@ -6,19 +6,9 @@
 //     K~[i,k] += v * D[j,l]           K~[i,l] += v * D[j,k]
 //     K~[j,k] += v * D[i,l]           K~[j,l] += v * D[i,k]           (per spin density)
 //     J = J~ + J~^T,  K = K~ + K~^T.
-//
-// Kernel shape (HBM-bound streaming kernel, no tensor cores):
-//   * a WARP is the unit of work.  A warp task is (k-range of JK_KN sub-rows) x (l-chunk of 64 columns,
-//     two per lane -> one 128-bit load per lane per row) x (a list of row-blocks of NI x NJ rows (i,j)).
-//   * everything an integral touches lives in registers: D[j,l], D[i,l] lane operands, the K~[i,l], K~[j,l]
-//     and J~[i,j] accumulators; D[i,k], D[j,k], D2[i,j] are warp-uniform; K~[i,k], K~[j,k] are reduced
-//     across lanes with a multi-value shuffle butterfly once per sub-row.
-//   * J~[k,l] is accumulated across ALL row-blocks of the task in a per-warp shared-memory slab next to the
-//     TMA-free staged D2[k,l] tile (exclusive ownership -> plain read-modify-write, no shared atomics).
-//   * flushes to the global J~/K~ work matrices use red.global.add.f64; they amount to ~2% of the
-//     streamed elements.
-//   * persistent grid (SM count x resident CTAs), tasks pulled from an atomic counter; adjacent task ids
-//     are adjacent l-chunks of the same rows, so concurrently running warps stream adjacent addresses.
+// The streaming kernel is in jk_stream.cuh (HBM-bound, no tensor cores: 1.5 flop per byte); this file holds the
+// schedule, the prep / finalize kernels, the cross-check kernel and the launch logic.
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -26,10 +16,7 @@
 namespace sqcc {
 
 struct JKParams {
-    const double *P;
-    const int64_t *rowoff;  // [nrows + 1] shard-relative offsets of the held rows (simple kernel)
-    const int64_t *rowij;   // [nrows] pair index of the held rows (simple kernel)
-    const int64_t *ioff;    // [n] shard-relative: row (i, j) starts at ioff[i] + j Te(i) + Te(j) (held rows only)
+    const double *P;    // this rank's shard (tile range) of the native v2 tensor
     int n, ldd;
     const double *d2;   // [n][ldd]   2*(Da+Db)
     const double *dsp;  // [nspin][n][ldd]
@@ -39,48 +26,41 @@ struct JKParams {
     const RowBlock *rowblocks;
     int ntasks;
     unsigned int *counter;
+    double fx_scale;            // deterministic mode: 2^shift of the fixed-point accumulators
     unsigned long long *trace;  // optional (tuning): per warp {first task start, last task end, tasks done} in ns
 };
 
-__device__ __forceinline__ double2 ldg_stream(const double *p)
-{
-    double2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
-__device__ __forceinline__ void red_add(double *p, double v)
-{
-    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
 
 }  // namespace sqcc
-#include "jk_pipe.cuh"
+#include "jk_stream.cuh"
 namespace sqcc {
 
-// ---- simple cross-check kernel: one CTA per row, one global atomic per contribution ------------------
+// ---- cross-check kernel: storage order, one global atomic per contribution ---------------------------------
 template <int NSPIN, bool WANTK>
-__global__ void __launch_bounds__(256) jk_simple_kernel(const JKParams p, int64_t nrows)
+__global__ void __launch_bounds__(256) jk_simple_kernel(const JKParams p, const int64_t *__restrict__ ibase,
+                                                        const int64_t *__restrict__ tfirst, int64_t t_lo, int64_t t_hi,
+                                                        int64_t shard_base)
 {
     const int n = p.n, ldd = p.ldd;
     const size_t nl = (size_t)n * ldd;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
-        const int64_t ij = p.rowij[row];
-        int i = (int)((sqrt(8.0 * (double)ij + 1.0) - 1.0) * 0.5);
-        while (pair_index(i, 0) > ij) --i;
-        while (pair_index(i + 1, 0) <= ij) ++i;
-        const int j = (int)(ij - pair_index(i, 0));
-        const double *base = p.P + p.rowoff[row];
-        const double d2ij = p.d2[(size_t)i * ldd + j];
-        double jrow = 0.0;
-        for (int k = warp; k <= i; k += nwarps) {
-            const int lmax = k < i ? k : j;
-            const double *sub = base + subrow_offset(k);
-            for (int l = lane; l <= lmax; l += 32) {
-                const double v = sub[l];
-                jrow += v * p.d2[(size_t)k * ldd + l];
-                atomicAdd(p.jt + (size_t)k * ldd + l, v * d2ij);
+    const int c = blockIdx.y;
+    int ib = 0;
+    for (int64_t t = t_lo + blockIdx.x; t < t_hi; t += gridDim.x) {
+        while (tfirst[ib + 1] <= t) ++ib;
+        const int ihi = lay_ihi(n, ib), imax = ihi - 1, jb = (int)(t - tfirst[ib]);
+        if (LAY_CHUNK * c > imax) continue;
+        const double *tile = p.P + (ibase[ib] + (int64_t)jb * lay_tile_len(imax) - shard_base);
+        for (int k = LAY_CHUNK * c; k <= imax; ++k) {
+            const int w = lay_w(k - LAY_CHUNK * c);
+            const double *piece = tile + lay_piece_offset(imax, c, k);
+            for (int e = threadIdx.x; e < LAY_ROWS * w; e += blockDim.x) {
+                const int r = e / w, x = e - r * w;
+                const int i = ihi - 4 + (r & 3), j = 4 * jb + (r >> 2), l = LAY_CHUNK * c + x;
+                if (!(i >= 0 && j <= i && k <= i && l <= (k < i ? k : j))) continue;
+                const double v = piece[e];
+                atomicAdd(p.jt + (size_t)i * ldd + j, v * p.d2[(size_t)k * ldd + l]);
+                atomicAdd(p.jt + (size_t)k * ldd + l, v * p.d2[(size_t)i * ldd + j]);
                 if (WANTK) {
 #pragma unroll
                     for (int s = 0; s < NSPIN; ++s) {
@@ -94,40 +74,67 @@ __global__ void __launch_bounds__(256) jk_simple_kernel(const JKParams p, int64_
                 }
             }
         }
-        atomicAdd(p.jt + (size_t)i * ldd + j, jrow);
     }
 }
 
 // ---- prep / finalize ---------------------------------------------------------------------------------
+// dsum (optional, deterministic mode): [3] sums of |D2|, |Da|, |Db| accumulated with integer atomics on the raw
+// bit patterns is not possible, so they are ordinary float atomics -- they only size the fixed-point scale, which is
+// then rounded DOWN to a power of two with two guard bits, so last-bit differences of the sums never change it.
 __global__ void jk_prep_kernel(const double *__restrict__ D, int nspin, int n, int ldd, double *__restrict__ dwork,
-                               double *__restrict__ acc, unsigned int *counter)
+                               double *__restrict__ acc, unsigned int *counter, double *__restrict__ dsum)
 {
     const size_t nl = (size_t)n * ldd;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx == 0) *counter = 0u;
-    if (idx >= nl) return;
-    const int r = (int)(idx / ldd), c = (int)(idx % ldd);
     double da = 0.0, db = 0.0;
-    if (c < n) {
-        da = D[(size_t)r * n + c];
-        if (nspin == 2) db = D[(size_t)n * n + (size_t)r * n + c];
+    if (idx < nl) {
+        const int r = (int)(idx / ldd), c = (int)(idx % ldd);
+        if (c < n) {
+            da = D[(size_t)r * n + c];
+            if (nspin == 2) db = D[(size_t)n * n + (size_t)r * n + c];
+        }
+        dwork[idx] = 2.0 * (da + db);
+        dwork[nl + idx] = da;
+        dwork[2 * nl + idx] = db;
+        acc[idx] = 0.0;
+        acc[nl + idx] = 0.0;
+        acc[2 * nl + idx] = 0.0;
     }
-    dwork[idx] = 2.0 * (da + db);
-    dwork[nl + idx] = da;
-    dwork[2 * nl + idx] = db;
-    acc[idx] = 0.0;
-    acc[nl + idx] = 0.0;
-    acc[2 * nl + idx] = 0.0;
+    if (dsum) {
+        double s2 = fabs(2.0 * (da + db)), sa = fabs(da), sb = fabs(db);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(dsum, s2);
+            atomicAdd(dsum + 1, sa);
+            atomicAdd(dsum + 2, sb);
+        }
+    }
 }
 
+// J = J~ + J~^T, K = K~ + K~^T.  inv_scale != 0: the accumulators are 64-bit fixed point (deterministic mode).
 __global__ void jk_finalize_kernel(const double *__restrict__ acc, int nspin, int want_k, int n, int ldd,
-                                   double *__restrict__ J, double *__restrict__ K)
+                                   double *__restrict__ J, double *__restrict__ K, double inv_scale)
 {
     const size_t nl = (size_t)n * ldd;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n * n) return;
     const int pr = (int)(idx / n), q = (int)(idx % n);
     const int hi = pr >= q ? pr : q, lo = pr >= q ? q : pr;
+    if (inv_scale != 0.0) {
+        const long long *a = reinterpret_cast<const long long *>(acc);
+        const long long jt = a[(size_t)hi * ldd + lo];
+        J[idx] = (double)(pr == q ? 2 * jt : jt) * inv_scale;
+        if (want_k)
+            for (int s = 0; s < nspin; ++s)
+                K[(size_t)s * n * n + idx] = (double)(a[(1 + s) * nl + (size_t)pr * ldd + q] + a[(1 + s) * nl + (size_t)q * ldd + pr]) * inv_scale;
+        return;
+    }
     const double jt = acc[(size_t)hi * ldd + lo];
     J[idx] = pr == q ? 2.0 * jt : jt;
     if (want_k) {
@@ -138,28 +145,35 @@ __global__ void jk_finalize_kernel(const double *__restrict__ acc, int nspin, in
     }
 }
 
-// ---- host side -----------------------------------------------------------------------------------------
-static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int ni, int nj)
+// max |stored value| of the shard (deterministic mode, once per attached tensor)
+__global__ void __launch_bounds__(256) eri_absmax_kernel(const double *__restrict__ P, int64_t len, unsigned long long *out)
 {
-    sc.ni = ni;
-    sc.nj = nj;
+    double m = 0.0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < len; t += (int64_t)gridDim.x * blockDim.x)
+        m = fmax(m, fabs(P[t]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));   // non-negative doubles order like integers
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int nb)
+{
+    sc.nb = nb;
     sc.h_rowblocks.clear();
     sc.h_tasks.clear();
     const int n = ctx->n;
-    // row-blocks: i-blocks anchored at the top of the i range (the longest rows sit in full blocks; the clipped block
-    // is the one at i = 0), i0 descending (long rows first), j0 ascending; blocks without a held row are dropped
-    for (int i0 = n - ni; i0 > -ni; i0 -= ni) {
-        const int ilo = i0 < 0 ? 0 : i0;   // the lowest block is stored as i0 = 0 with its upper rows masked off
-        const int ihi = i0 + ni;           // one past the last i of the block
-        if (ihi <= ctx->i_begin || ilo >= ctx->i_end) continue;
-        for (int j0 = 0; j0 <= ihi - 1; j0 += nj) {
-            unsigned int mask = 0;
-            for (int a = 0; a < ni; ++a)
-                for (int b = 0; b < nj; ++b) {
-                    const int i = ilo + a, j = j0 + b;
-                    if (i < ihi && i < n && j >= ctx->jlo[i] && j < ctx->jhi[i]) mask |= 1u << (a * nj + b);
-                }
-            if (mask) sc.h_rowblocks.push_back({ilo, j0, mask, 0});
+    const int nib = lay_nblocks(n);
+    // row-blocks of the held tiles: i-blocks descending (long rows first), j ascending.  The 4 x 2 shape makes two
+    // row-blocks out of a tile (its halves b < 2 / b >= 2); a half whose rows all lie above the diagonal is dropped.
+    for (int ib = nib - 1; ib >= 0; --ib) {
+        const int imax = lay_ihi(n, ib) - 1;
+        const int64_t t0 = ctx->h_tfirst[ib], t1 = ctx->h_tfirst[ib + 1];
+        const int64_t a = t0 > ctx->t_begin ? t0 : ctx->t_begin, b = t1 < ctx->t_end ? t1 : ctx->t_end;
+        for (int64_t t = a; t < b; ++t) {
+            const int jb = (int)(t - t0);
+            const int64_t base = ctx->h_ibase[ib] + (int64_t)jb * lay_tile_len(imax) - ctx->shard_base;
+            for (int j0 = 4 * jb; j0 < 4 * jb + 4 && j0 <= imax; j0 += nb) sc.h_rowblocks.push_back({base, imax, j0});
         }
     }
     const int nrb = (int)sc.h_rowblocks.size();
@@ -177,36 +191,31 @@ static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int ni, int nj)
     }
     // Guided grouping: a task lasts ~(row-blocks in its group) x 16 sub-rows, and nearly all (k-range, chunk) tasks of a
     // group are full-size, so with a fixed group the last, partially filled wave of tasks idles most warps for one task
-    // duration (~85 us of a 0.53 ms kernel at N = 222, ~90 us of the 1.26 ms shards at 8 GPUs).  The group therefore
-    // shrinks towards the end of the list: never more row-blocks than would leave `tail_waves` tasks per resident warp.
-    std::vector<int64_t> cells_after(nrb + 1, 0);   // (k-range, chunk) cells of row-blocks g .. nrb-1
-    for (int g = nrb - 1; g >= 0; --g) {
-        int imax = sc.h_rowblocks[g].i0 + ni - 1;
-        if (imax > n - 1) imax = n - 1;
+    // duration.  The group therefore shrinks towards the end of the list: never more row-blocks than would leave
+    // `tail_waves` tasks per resident warp.
+    auto cells_of = [&](int imax) {   // (k-range, chunk) tasks of one row-block: chunks c with 64 c <= k0
         int64_t t = 0;
-        for (int k0 = 0; k0 <= imax; k0 += JK_KN) t += (k0 + JK_KN - 1 < imax ? k0 + JK_KN - 1 : imax) / JK_CHUNK + 1;
-        cells_after[g] = cells_after[g + 1] + t;
-    }
+        for (int k0 = 0; k0 <= imax; k0 += JK_KN) t += k0 / JK_CHUNK + 1;
+        return t;
+    };
+    std::vector<int64_t> cells_after(nrb + 1, 0);
+    for (int g = nrb - 1; g >= 0; --g) cells_after[g] = cells_after[g + 1] + cells_of(sc.h_rowblocks[g].imax);
     const int64_t resident = (int64_t)ctx->sm_count * 8;
     const double tail_waves = getenv("SQCC_JK_TAIL") ? atof(getenv("SQCC_JK_TAIL")) : 2.0;
     for (int g0 = 0; g0 < nrb;) {
         int gsz = group;
         if (tail_waves > 0.0) {
-            // cells_after / gsz tasks remain if the rest is cut in groups of gsz: keep that above tail_waves x resident
             const int64_t lim = (int64_t)((double)cells_after[g0] / (tail_waves * (double)resident));
             if (lim < gsz) gsz = (int)(lim < 1 ? 1 : lim);
         }
         int g1 = g0 + gsz < nrb ? g0 + gsz : nrb;
-        // largest i in this group (list is i0-descending): first entry
-        int imax = sc.h_rowblocks[g0].i0 + ni - 1;
-        if (imax > n - 1) imax = n - 1;
+        const int imax = sc.h_rowblocks[g0].imax;   // largest i of the group (list is i-descending)
         for (int k0 = 0; k0 <= imax; k0 += JK_KN) {
-            // restrict to row-blocks of the group that contain some i >= k0 (a prefix of the group)
+            // row-blocks of the group that have sub-rows k >= k0 (a prefix of the group)
             int cnt = 0;
-            while (g0 + cnt < g1 && sc.h_rowblocks[g0 + cnt].i0 + ni - 1 >= k0) ++cnt;
+            while (g0 + cnt < g1 && sc.h_rowblocks[g0 + cnt].imax >= k0) ++cnt;
             if (cnt == 0) continue;
-            int kmax = k0 + JK_KN - 1 < imax ? k0 + JK_KN - 1 : imax;
-            for (int c = 0; c * JK_CHUNK <= kmax; ++c) sc.h_tasks.push_back({k0, c, g0, cnt});
+            for (int c = 0; c * JK_CHUNK <= k0; ++c) sc.h_tasks.push_back({k0, c, g0, cnt});
         }
         g0 = g1;
     }
@@ -227,44 +236,29 @@ static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int ni, int nj)
 
 int jk_build_schedule(sqcc_ctx *ctx)
 {
-    SQCC_TRY(build_one_schedule(ctx, ctx->sched[0], JK_NI, JK_NJ));
-    SQCC_TRY(build_one_schedule(ctx, ctx->sched[1], 2, 2));
-    SQCC_TRY(build_one_schedule(ctx, ctx->sched[2], 4, 4));
+    SQCC_TRY(build_one_schedule(ctx, ctx->sched[0], 4));
+    SQCC_TRY(build_one_schedule(ctx, ctx->sched[1], 2));
     const size_t nl = (size_t)ctx->n * ctx->ldd;
     if (ctx->d_dwork) cudaFree(ctx->d_dwork);
     ctx->d_dwork = nullptr;
-    SQCC_CUDA(cudaMalloc(&ctx->d_dwork, sizeof(double) * 3 * nl));
+    // [3][N][ldd] + one chunk of slack (the density tile loads of the last rows never leave the allocation) + [4] sums
+    SQCC_CUDA(cudaMalloc(&ctx->d_dwork, sizeof(double) * (3 * nl + JK_CHUNK + 4)));
+    SQCC_CUDA(cudaMemsetAsync(ctx->d_dwork, 0, sizeof(double) * (3 * nl + JK_CHUNK + 4), ctx->stream));
     SQCC_TRY(comm_alloc(ctx));   // accumulators live in the peer-mappable exchange region
-    if (!ctx->d_counter) SQCC_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+    if (!ctx->d_counter) SQCC_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned long long) * 2));
+    ctx->eri_absmax = -1.0;
     return SQCC_OK;
 }
 
-template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES, bool SLAB, bool RING>
-static int launch_pipe_cfg(sqcc_ctx *ctx, const JKParams &p);
-
-// (WARPS, STAGES) of the pipelined kernel: tuning knob jk_cfg (0 = default).
-template <int NI, int NJ, int NSPIN, bool WANTK>
-static int launch_pipe(sqcc_ctx *ctx, const JKParams &p)
+template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, int PF>
+static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
 {
-    switch (ctx->jk_cfg) {
-    case 1: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 12, 3, false, true>(ctx, p);
-    case 2: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 8, 3, true, true>(ctx, p);
-    case 3: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 8, 1, true, false>(ctx, p);
-    default: return launch_pipe_cfg<NI, NJ, NSPIN, WANTK, 11, 2, true, true>(ctx, p);
-    }
-}
-
-template <int NI, int NJ, int NSPIN, bool WANTK, int WARPS, int STAGES, bool SLAB, bool RING>
-static int launch_pipe_cfg(sqcc_ctx *ctx, const JKParams &p)
-{
-    constexpr int NVP = ((WANTK ? NSPIN : 1) * (NI + NJ) + 7) / 8;
-    const size_t smem = (size_t)WARPS * jk_pipe_warp_bytes<NI, NJ, STAGES, SLAB, RING, NVP>();
-    auto kern = jk_pipe_kernel<NI, NJ, NSPIN, WANTK, WARPS, STAGES, SLAB, RING>;
+    using SM = JKSmem<NB, WANTK ? NSPIN : 1, STAGES>;
+    const size_t smem = (size_t)WARPS * SM::WARP_BYTES;
+    static_assert((size_t)WARPS * SM::WARP_BYTES <= 232448, "shared memory per CTA");
+    auto kern = jk_stream_kernel<NB, NSPIN, WANTK, WARPS, STAGES, TMA, FIXED, PF>;
     SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SQCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
-    if (per_sm < 1) per_sm = 1;
-    int grid = ctx->sm_count * per_sm;
+    int grid = ctx->sm_count;
     int max_useful = (p.ntasks + WARPS - 1) / WARPS;
     if (grid > max_useful) grid = max_useful > 0 ? max_useful : 1;
     kern<<<grid, WARPS * 32, smem, ctx->stream>>>(p);
@@ -274,30 +268,70 @@ static int launch_pipe_cfg(sqcc_ctx *ctx, const JKParams &p)
     return SQCC_OK;
 }
 
+template <int NB, int NSPIN, bool WANTK, int STAGES>
+static int launch_stream_cfg(sqcc_ctx *ctx, const JKParams &p)
+{
+    // cfg 0: TMA ring (default)   1: cp.async ring for every piece (A/B of the TMA path)   2: TMA + L2 prefetch 2 pieces ahead
+    if (ctx->jk_fixed) return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, true, 0>(ctx, p);
+    switch (ctx->jk_cfg) {
+    case 1: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, false, false, 0>(ctx, p);
+    case 2: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, 2>(ctx, p);
+    default: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, 0>(ctx, p);
+    }
+}
+
+// deterministic mode: fixed-point scale 2^s with |every partial sum| * 2^s < 2^61
+static int fixed_scale(sqcc_ctx *ctx, int nspin, double *scale)
+{
+    const size_t nl = (size_t)ctx->n * ctx->ldd;
+    if (ctx->eri_absmax < 0.0) {
+        unsigned long long *d_m = reinterpret_cast<unsigned long long *>(ctx->d_counter) + 1;
+        SQCC_CUDA(cudaMemsetAsync(d_m, 0, sizeof(unsigned long long), ctx->stream));
+        eri_absmax_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->native_len, d_m);
+        ctx->launches++;
+        unsigned long long bits = 0;
+        SQCC_CUDA(cudaMemcpyAsync(&bits, d_m, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+        SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+        double m;
+        memcpy(&m, &bits, sizeof(m));
+        ctx->eri_absmax = m;
+    }
+    double sums[3];
+    SQCC_CUDA(cudaMemcpyAsync(sums, ctx->d_dwork + 3 * nl + JK_CHUNK, sizeof(sums), cudaMemcpyDeviceToHost, ctx->stream));
+    SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
+    double dmax = sums[0] > sums[1] ? sums[0] : sums[1];
+    if (nspin == 2 && sums[2] > dmax) dmax = sums[2];
+    const double bound = ctx->eri_absmax * dmax;
+    SQCC_REQUIRE(isfinite(bound), "non-finite operands in deterministic J/K mode");
+    int e = 0;
+    if (bound > 0.0) frexp(bound, &e);   // bound < 2^e
+    // two guard bits: the sums come from float atomics and may differ in the last bits between runs and ranks; the
+    // exponent only changes when a sum sits on a power of two, which the guard bits absorb on the safe side
+    int shift = 59 - e;
+    if (shift > 1000) shift = 1000;
+    *scale = ldexp(1.0, shift);
+    return SQCC_OK;
+}
+
 // prep + the fused kernel: leaves this rank's partial J~/K~ in the context's accumulators
 int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
 {
-    SQCC_REQUIRE(ctx->d_eri, "no ERI attached (sqcc_eri_attach)");
+    SQCC_REQUIRE(ctx->d_eri, "no ERI attached (sqcc_eri_attach_tiles)");
     SQCC_REQUIRE(nspin == 1 || nspin == 2, "nspin must be 1 or 2");
     SQCC_REQUIRE(d_D, "null D pointer");
     const int n = ctx->n, ldd = ctx->ldd;
     const size_t nl = (size_t)n * ldd;
+    double *dsum = ctx->jk_fixed ? ctx->d_dwork + 3 * nl + JK_CHUNK : nullptr;
+    if (dsum) SQCC_CUDA(cudaMemsetAsync(dsum, 0, 4 * sizeof(double), ctx->stream));
     jk_prep_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, ctx->stream>>>(d_D, nspin, n, ldd, ctx->d_dwork, ctx->d_acc,
-                                                                         ctx->d_counter);
+                                                                         ctx->d_counter, dsum);
     ctx->launches++;
     SQCC_CUDA(cudaGetLastError());
 
-    // default: 4x4 row-blocks (RHF, J-only), 2x2 for the dual-density UHF pass; cfg 1..3 select 4x2 tuning variants
-    if (ctx->jk_variant == 2) ctx->jk_cfg = 3;   // direct 128-bit global loads (no shared-memory ring)
-    const bool wide = ctx->jk_variant == 0 && (ctx->jk_cfg == 0 || ctx->jk_cfg == 4) && !(nspin == 2 && want_k);
     const bool uhf = nspin == 2 && want_k;
-    const bool uhf_wide = uhf && ctx->jk_variant == 0 && ctx->jk_cfg != 5;   // 4x2 row-blocks, two reduction passes
-    const JKSchedule &sc = ctx->sched[uhf ? (uhf_wide ? 0 : 1) : (wide ? 2 : 0)];
+    const JKSchedule &sc = ctx->sched[uhf ? 1 : 0];
     JKParams p;
     p.P = ctx->d_eri;
-    p.rowoff = ctx->d_rowoff;
-    p.rowij = ctx->d_rowij;
-    p.ioff = ctx->d_ioff;
     p.n = n;
     p.ldd = ldd;
     p.d2 = ctx->d_dwork;
@@ -309,34 +343,34 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
     p.ntasks = sc.n_tasks;
     p.counter = ctx->d_counter;
     p.trace = ctx->d_trace;
+    p.fx_scale = 0.0;
+    ctx->fx_scale = 0.0;
+    if (ctx->jk_fixed) {
+        SQCC_REQUIRE(ctx->jk_variant == 0, "the deterministic mode uses the streaming kernel (variant 0)");
+        SQCC_TRY(fixed_scale(ctx, nspin, &p.fx_scale));
+        ctx->fx_scale = p.fx_scale;
+    }
 
     SQCC_TRY(timer_start(ctx, 0));
     if (ctx->jk_variant == 1) {
-        int64_t nrows = ctx->nrows;
-        int grid = (int)(nrows < (int64_t)ctx->sm_count * 8 ? nrows : (int64_t)ctx->sm_count * 8);
-        if (grid < 1) grid = 1;
+        const int64_t tiles = ctx->t_end - ctx->t_begin;
+        const dim3 grid((unsigned)(tiles < (int64_t)ctx->sm_count * 4 ? (tiles > 0 ? tiles : 1) : (int64_t)ctx->sm_count * 4),
+                        (unsigned)((n - 1) / LAY_CHUNK + 1));
         if (!want_k)
-            jk_simple_kernel<1, false><<<grid, 256, 0, ctx->stream>>>(p, nrows);
+            jk_simple_kernel<1, false><<<grid, 256, 0, ctx->stream>>>(p, ctx->d_ibase, ctx->d_tfirst, ctx->t_begin, ctx->t_end, ctx->shard_base);
         else if (nspin == 1)
-            jk_simple_kernel<1, true><<<grid, 256, 0, ctx->stream>>>(p, nrows);
+            jk_simple_kernel<1, true><<<grid, 256, 0, ctx->stream>>>(p, ctx->d_ibase, ctx->d_tfirst, ctx->t_begin, ctx->t_end, ctx->shard_base);
         else
-            jk_simple_kernel<2, true><<<grid, 256, 0, ctx->stream>>>(p, nrows);
+            jk_simple_kernel<2, true><<<grid, 256, 0, ctx->stream>>>(p, ctx->d_ibase, ctx->d_tfirst, ctx->t_begin, ctx->t_end, ctx->shard_base);
         ctx->launches++;
         SQCC_CUDA(cudaGetLastError());
-    } else if (uhf_wide && p.ntasks > 0) {
-        SQCC_TRY((launch_pipe_cfg<4, 2, 2, true, 8, 2, true, true>(ctx, p)));   // a deeper ring changes nothing (profiles/)
-    } else if (wide && p.ntasks > 0) {
-        if (!want_k)
-            SQCC_TRY((launch_pipe_cfg<4, 4, 1, false, 8, 2, true, true>(ctx, p)));
-        else
-            SQCC_TRY((launch_pipe_cfg<4, 4, 1, true, 8, 2, true, true>(ctx, p)));
     } else if (p.ntasks > 0) {
-        if (!want_k)
-            SQCC_TRY((launch_pipe<JK_NI, JK_NJ, 1, false>(ctx, p)));
-        else if (nspin == 1)
-            SQCC_TRY((launch_pipe<JK_NI, JK_NJ, 1, true>(ctx, p)));
+        if (uhf)
+            SQCC_TRY((launch_stream_cfg<2, 2, true, 3>(ctx, p)));
+        else if (!want_k)
+            SQCC_TRY((launch_stream_cfg<4, 1, false, 2>(ctx, p)));
         else
-            SQCC_TRY((launch_pipe<2, 2, 2, true>(ctx, p)));
+            SQCC_TRY((launch_stream_cfg<4, 1, true, 2>(ctx, p)));
     }
     SQCC_TRY(timer_stop(ctx, 0));
     return SQCC_OK;
@@ -354,8 +388,8 @@ int jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_
         SQCC_TRY(timer_stop(ctx, 1));
         return SQCC_OK;
     }
-    jk_finalize_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_acc, nspin, want_k, n,
-                                                                                         ldd, d_J, d_K);
+    jk_finalize_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->d_acc, nspin, want_k, n, ldd, d_J, d_K, ctx->fx_scale != 0.0 ? 1.0 / ctx->fx_scale : 0.0);
     ctx->launches++;
     SQCC_CUDA(cudaGetLastError());
     SQCC_TRY(timer_stop(ctx, 1));

@@ -1,0 +1,536 @@
+// Fused J/K kernel over the native v2 layout (layout.cuh).  Included by jk_fused.cu.
+//
+// A WARP is the unit of work.  A warp task is (16 sub-rows k) x (one 64-column chunk, two columns per lane) x (a list
+// of row-blocks: 4 rows i x NB rows j of one tile, NB = 4 for the single-density passes, 2 for the dual-density UHF
+// pass).  In the v2 layout the R = 4 NB rows of a row-block for one (k, chunk) are ONE contiguous piece and the 16
+// sub-rows of a task follow each other, so the ERI stream of a task is a single running pointer:
+//   * full pieces (64 columns): one elected lane issues ONE cp.async.bulk (TMA) per pipeline stage into the warp's
+//     shared-memory ring, completion on a per-stage mbarrier (UBLKCP in SASS);
+//   * the triangular edge (pieces of 16 / 32 / 48 columns, k - 64 c < 48): 16-byte cp.async per lane with immediate
+//     row offsets and the zero-fill form for the lanes past the piece, landing in the same [R][64] stage layout.
+// Cells outside the canonical range are stored as 0.0, so the consumer is mask free and has no per-row address
+// arithmetic at all.
+//
+// Consumer, per sub-row: every lane holds D[j,l], D[i,l] (its two columns), the accumulators K~[i,l], K~[j,l], J~[i,j];
+// D[i,k], D[j,k] and D2[i,j] are warp-uniform (staged per row-block in shared memory, broadcast loads); J~[k,l] goes
+// to a warp-private slab that lives for the whole task.  K~[i,k], K~[j,k] need a sum over the lanes once per sub-row;
+// that reduction is SOFTWARE-PIPELINED over three iterations so that the loop body is one straight-line block in which
+// ptxas can place all the shuffles / shared-memory round trips in the issue slots the half-rate DFMAs leave free:
+//     iteration kk:   A  the 12 R DFMAs of sub-row kk                                    -> lane partials cd(kk)
+//                     B  xor-16 shuffle of cd(kk-1), 16 lanes store them (transposed)     -> s_red[(kk-1) & 1]
+//                     C  partials of kk-2: 4 loads, 3 adds, 2 shuffles, one store         -> s_kout[.][kk-2]
+// and the 16 x NV reduced values of a row-block leave with coalesced red.global.add.f64 after its sweep.
+#pragma once
+
+namespace sqcc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MBAR_DONE_%=;\n\t"
+        "bra MBAR_WAIT_%=;\n\t"
+        "MBAR_DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// one contiguous global -> shared bulk copy (TMA), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// xor-shuffle of a double without the volatile mov.b64 pack/unpack of the CUDA header
+__device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, lane_mask);
+    hi = __shfl_xor_sync(0xffffffffu, hi, lane_mask);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Flushes to the global work matrices.  FIXED = false: red.global.add.f64 (result depends on the arrival order in the
+// last bits).  FIXED = true: the value is converted to 64-bit fixed point (scale 2^fx_shift, chosen by the prep kernel
+// from the operand magnitudes) and added with an integer red: integer addition is associative, so the sums -- and
+// with them J and K -- are bit-for-bit reproducible from run to run and independent of the task schedule.
+template <bool FIXED>
+__device__ __forceinline__ void flush_add(bool pred, double *ptr, double v, double fx_scale)
+{
+    if (pred) {
+        if (FIXED) {
+            const long long q = __double2ll_rn(v * fx_scale);
+            asm volatile("red.global.add.u64 [%0], %1;" ::"l"(ptr), "l"(q) : "memory");
+        } else {
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(ptr), "d"(v) : "memory");
+        }
+    }
+}
+
+constexpr int JK_RED_STRIDE = 17;  // value stride of the reduction scratch (odd: conflict-free 4x4 read pattern)
+
+template <int NB, int NS, int STAGES>
+struct JKSmem {
+    static constexpr int R = 4 * NB;
+    static constexpr int NV = NS * (4 + NB);          // lane-partial values reduced per sub-row
+    static constexpr int NVE = (NV + 1) & ~1;
+    static constexpr int STAGE_BYTES = R * 512;
+    static constexpr int RED_BUF = (NV > 8 ? NV : 8) * JK_RED_STRIDE;   // doubles per buffer (>= 8 values: J~ row dots go 8 at a time)
+    static constexpr int OFF_SLAB = 0;                                   // double2 [16][32]
+    static constexpr int OFF_RING = OFF_SLAB + JK_KN * 512;              // [STAGES][R][512 B]
+    static constexpr int OFF_U = OFF_RING + STAGES * STAGE_BYTES;        // double [16][NVE]
+    static constexpr int OFF_RED = OFF_U + JK_KN * NVE * 8;              // double [2][RED_BUF]
+    static constexpr int OFF_KOUT = OFF_RED + 2 * RED_BUF * 8;           // double [NVE][17]
+    static constexpr int OFF_W = OFF_KOUT + NVE * JK_RED_STRIDE * 8;     // double [R]
+    static constexpr int OFF_BAR = OFF_W + R * 8;                        // u64 [STAGES]
+    static constexpr int WARP_BYTES = (OFF_BAR + STAGES * 8 + 63) & ~63;
+};
+
+// NB: rows j per row-block (4: RHF / J-only, 2: UHF).  TMA: full pieces through cp.async.bulk (false: cp.async only).
+// PF: pieces of L2 prefetch distance ahead of the ring (0: none).
+template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, int PF>
+__global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams p)
+{
+    constexpr int NI = 4;
+    constexpr int NS = WANTK ? NSPIN : 1;
+    using SM = JKSmem<NB, NS, STAGES>;
+    constexpr int R = SM::R, NV = SM::NV, NVE = SM::NVE;
+    constexpr int NVP = (NV + 7) / 8;
+    constexpr uint32_t STAGE_BYTES = SM::STAGE_BYTES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wbase = smem_raw + (size_t)warp * SM::WARP_BYTES;
+    double2 *s_jt = reinterpret_cast<double2 *>(wbase + SM::OFF_SLAB);
+    const double2 *ring = reinterpret_cast<const double2 *>(wbase + SM::OFF_RING);
+    double *s_u = reinterpret_cast<double *>(wbase + SM::OFF_U);
+    double *s_red = reinterpret_cast<double *>(wbase + SM::OFF_RED);
+    double *s_kout = reinterpret_cast<double *>(wbase + SM::OFF_KOUT);
+    double *s_w = reinterpret_cast<double *>(wbase + SM::OFF_W);
+    const uint32_t ring_u32 = smem_u32(wbase + SM::OFF_RING);
+    const uint32_t bar_u32 = smem_u32(wbase + SM::OFF_BAR);
+    const int n = p.n, ldd = p.ldd;
+    const size_t nl = (size_t)n * ldd;
+    const double fx = p.fx_scale;
+    uint32_t stage_w = 0, stage_r = 0, phase_bits = 0;   // ring write / read positions and mbarrier parities, persist across tasks
+    unsigned long long tr_start = 0, tr_tasks = 0;
+    if (p.trace) tr_start = globaltimer_ns();
+
+    if (TMA) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) mbar_init(bar_u32 + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
+
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(p.counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= (unsigned)p.ntasks) break;
+        const JKTask task = p.tasks[t];
+        const int k0 = task.k0, c = task.chunk;
+        const int cbase = c * JK_CHUNK;
+        const int l0 = cbase + 2 * lane;
+        const bool lane_in = l0 < ldd;
+        const int w = lay_w(k0 - cbase);                 // piece width of this task (uniform: k0, cbase multiples of 16)
+        const bool full = TMA && w == JK_CHUNK;
+        ++tr_tasks;
+
+#pragma unroll 4
+        for (int kk = 0; kk < JK_KN; ++kk) s_jt[kk * 32 + lane] = make_double2(0.0, 0.0);
+
+        // row-block list of the task, one entry per lane (rb_count <= 32)
+        long long my_base = 0;
+        int my_imax = k0, my_j0 = 0;
+        if (lane < task.rb_count) {
+            const RowBlock rbk = p.rowblocks[task.rb_begin + lane];
+            my_base = rbk.base;
+            my_imax = rbk.imax;
+            my_j0 = rbk.j0;
+        }
+        // sub-rows to stream in this task
+        int total_it = 0;
+        {
+            int cnt = lane < task.rb_count ? (my_imax + 1 - k0 < JK_KN ? my_imax + 1 - k0 : JK_KN) : 0;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            total_it = cnt;
+        }
+
+        // ---- producer: one piece (sub-row) per call
+        int prod_rbi = -1, prod_left = 0, prod_todo = total_it;
+        const char *prod_src = reinterpret_cast<const char *>(p.P);
+        const uint32_t lane_bytes = 2 * lane < w ? 16u : 0u;
+        auto issue_next = [&]() {
+            if (prod_left == 0) {   // next row-block of the list
+                ++prod_rbi;
+                const long long base = __shfl_sync(0xffffffffu, my_base, prod_rbi);
+                const int imax = __shfl_sync(0xffffffffu, my_imax, prod_rbi);
+                const int j0 = __shfl_sync(0xffffffffu, my_j0, prod_rbi);
+                prod_left = imax + 1 - k0 < JK_KN ? imax + 1 - k0 : JK_KN;
+                long long off = base + lay_piece_offset(imax, c, k0);
+                if (NB == 2) off += (long long)((j0 >> 1) & 1) * 8 * w;   // second 4 x 2 half of the tile's pieces
+                prod_src = reinterpret_cast<const char *>(p.P + off);
+            }
+            const uint32_t dst = ring_u32 + stage_w * STAGE_BYTES;
+            if (full) {
+                if (lane == 0) {
+                    const uint32_t bar = bar_u32 + 8 * stage_w;
+                    mbar_expect_tx(bar, STAGE_BYTES);
+                    bulk_g2s(dst, prod_src, STAGE_BYTES, bar);
+                    if (PF > 0 && prod_left > PF) bulk_prefetch_l2(prod_src + (size_t)PF * (LAY_ROWS * JK_CHUNK * 8), STAGE_BYTES);
+                }
+            } else {
+                const char *src = prod_src + 16 * lane;
+                const uint32_t d = dst + 16 * lane;
+                if (w == 64) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) cp_async16_zfill(d + r * 512, src + r * 64 * 8, lane_bytes);
+                } else if (w == 48) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) cp_async16_zfill(d + r * 512, src + r * 48 * 8, lane_bytes);
+                } else if (w == 32) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) cp_async16_zfill(d + r * 512, src + r * 32 * 8, lane_bytes);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) cp_async16_zfill(d + r * 512, src + r * 16 * 8, lane_bytes);
+                }
+            }
+            prod_src += (size_t)LAY_ROWS * 8 * w;
+            stage_w = (stage_w + 1 == STAGES) ? 0 : stage_w + 1;
+            --prod_left;
+            --prod_todo;
+        };
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            if (prod_todo > 0) issue_next();
+            if (!full) cp_async_commit();
+        }
+
+        int cur_i0 = -1000;
+        double2 accA[NS][NI], di[NS][NI];
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int a = 0; a < NI; ++a) accA[s][a] = di[s][a] = make_double2(0.0, 0.0);
+
+        auto flushA = [&]() {
+            if (WANTK && cur_i0 > -1000) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+#pragma unroll
+                    for (int a = 0; a < NI; ++a) {
+                        const int i = cur_i0 + a;
+                        const bool ok = lane_in && i >= 0;
+                        double *dst = p.kt + s * nl + (size_t)(ok ? i : 0) * ldd + (ok ? l0 : 0);
+                        flush_add<FIXED>(ok, dst, accA[s][a].x, fx);
+                        flush_add<FIXED>(ok, dst + 1, accA[s][a].y, fx);
+                    }
+            }
+        };
+
+        // reduction helpers (pass h handles values 8h .. 8h+7: value 8h + (lane >> 2), 4 lanes per value, 4 entries each)
+        const int red_rd_off = (lane >> 2) * JK_RED_STRIDE + (lane & 3) * 4;
+
+        for (int rbi = 0; rbi < task.rb_count; ++rbi) {
+            const int imax = __shfl_sync(0xffffffffu, my_imax, rbi), j0 = __shfl_sync(0xffffffffu, my_j0, rbi);
+            const int i0 = imax - 3;   // may be negative in the clipped lowest i-block: those rows hold zeros
+            const int nkk = imax + 1 - k0 < JK_KN ? imax + 1 - k0 : JK_KN;
+            if (i0 != cur_i0) {
+                flushA();
+                cur_i0 = i0;
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+#pragma unroll
+                    for (int a = 0; a < NI; ++a) {
+                        accA[s][a] = make_double2(0.0, 0.0);
+                        if (WANTK)
+                            di[s][a] = (i0 + a >= 0 && lane_in) ? ldg2(p.dsp + s * nl + (size_t)(i0 + a) * ldd + l0)
+                                                                 : make_double2(0.0, 0.0);
+                    }
+            }
+            double2 dj[NS][NB], accB[NS][NB];
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    accB[s][b] = make_double2(0.0, 0.0);
+                    dj[s][b] = make_double2(0.0, 0.0);
+                    if (WANTK && j0 + b < n && lane_in) dj[s][b] = ldg2(p.dsp + s * nl + (size_t)(j0 + b) * ldd + l0);
+                }
+            double accJ[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) accJ[r] = 0.0;
+            // stage the warp-uniform operands of this row-block in shared memory (row indices clamped into range: operands of
+            // rows outside the canonical range only ever meet stored zeros):
+            //   s_w[r]      = D2[i_a, j_b], r = 4 b + a
+            //   s_u[kk][q]  = D_s[row_q, k0+kk], q = s*(NI+NB) + (a | NI+b)
+            __syncwarp();
+            if (lane < R) {
+                int i = i0 + (lane & 3), j = j0 + (lane >> 2);
+                i = i < 0 ? 0 : i;
+                j = j < n ? j : n - 1;
+                s_w[lane] = __ldg(p.d2 + (size_t)i * ldd + j);
+            }
+            if (WANTK && lane < JK_KN) {
+                // 32-bit indexing: nspin * n * ldd < 2^31 for every supported n
+                const int k = (k0 + lane) < n ? (k0 + lane) : n - 1;
+                const double *dk = p.dsp + k;
+                double *su = s_u + lane * NVE;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const int s = q / (NI + NB), wq = q % (NI + NB);
+                    int row = wq < NI ? i0 + wq : j0 + (wq - NI);
+                    row = row < 0 ? 0 : (row < n ? row : n - 1);
+                    su[q] = __ldg(dk + (s * n + row) * ldd);
+                }
+            }
+            // destinations of the reduced K~[row_q, k0 + kk] values: lane = kk + 16 (q & 1), pass m covers q = 2m, 2m+1
+            double *kout_dst[(NV + 1) / 2];
+            bool kout_ok[(NV + 1) / 2];
+#pragma unroll
+            for (int m = 0; m < (NV + 1) / 2; ++m) {
+                const int q = 2 * m + (lane >> 4);
+                const int s = q / (NI + NB), wq = q % (NI + NB);
+                const int row = wq < NI ? i0 + wq : j0 + (wq - NI);
+                kout_ok[m] = WANTK && q < NV && row >= 0 && row < n && (lane & 15) < nkk;
+                kout_dst[m] = p.kt + (kout_ok[m] ? s * nl + (size_t)row * ldd + k0 + (lane & 15) : 0);
+            }
+
+            double cdp[NV];   // lane partials of the previous sub-row, published one iteration later
+#pragma unroll
+            for (int q = 0; q < NV; ++q) cdp[q] = 0.0;
+            const double *d2p = p.d2 + (size_t)k0 * ldd + (lane_in ? l0 : 0);
+            double2 d2n = lane_in ? ldg2(d2p) : make_double2(0.0, 0.0);
+
+#pragma unroll 2
+            for (int kk = 0; kk < nkk; ++kk) {
+                __syncwarp();   // iteration kk-1 is complete in every lane: its ring stage is free, its s_red stores are visible
+                if (prod_todo > 0) issue_next();
+                if (full) {
+                    mbar_wait(bar_u32 + 8 * stage_r, (phase_bits >> stage_r) & 1u);
+                    phase_bits ^= 1u << stage_r;
+                } else {
+                    cp_async_commit();
+                    cp_async_wait<STAGES - 1>();   // this lane's 16 bytes of every row of the oldest stage have landed
+                }
+                __syncwarp();   // converged from here to the end of the body: no divergent branch below (ptxas can then
+                                // schedule the shuffles into the DFMA block instead of fencing them with BRA.DIV)
+                const double2 *buf = ring + (size_t)stage_r * (R * 32) + lane;
+                stage_r = (stage_r + 1 == STAGES) ? 0 : stage_r + 1;
+
+                // ---- C, loads: partials of sub-row kk-2 (buffer kk & 1); values past NV read a neighbour's (finite) data
+                double r4[NVP][4];
+                if (WANTK) {
+                    const double *rd = s_red + (kk & 1) * SM::RED_BUF + red_rd_off;
+#pragma unroll
+                    for (int h = 0; h < NVP; ++h)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) r4[h][e] = rd[(8 * h < NV - 8 ? 8 * h : (NV > 8 ? NV - 8 : 0)) * JK_RED_STRIDE + e];
+                }
+                // ---- A: the FMA block of sub-row kk
+                const double2 d2 = d2n;
+                d2p += ldd;
+                d2n = (lane_in && kk + 1 < nkk) ? ldg2(d2p) : make_double2(0.0, 0.0);
+                double u[NVE];
+                if (WANTK) {
+                    const double2 *up = reinterpret_cast<const double2 *>(s_u + kk * NVE);
+#pragma unroll
+                    for (int q = 0; q < NVE / 2; ++q) {
+                        const double2 t2 = up[q];
+                        u[2 * q] = t2.x;
+                        u[2 * q + 1] = t2.y;
+                    }
+                }
+                double2 jt2 = make_double2(0.0, 0.0);
+                double cd[NV];
+#pragma unroll
+                for (int q = 0; q < NV; ++q) cd[q] = 0.0;
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int a = 0; a < NI; ++a) {
+                        const int r = 4 * b + a;
+                        const double2 x = buf[r * 32];
+                        accJ[r] = fma(x.x, d2.x, fma(x.y, d2.y, accJ[r]));
+                        const double2 w2 = reinterpret_cast<const double2 *>(s_w)[r >> 1];
+                        const double wij = (r & 1) ? w2.y : w2.x;
+                        jt2.x = fma(x.x, wij, jt2.x);
+                        jt2.y = fma(x.y, wij, jt2.y);
+                        if (WANTK) {
+#pragma unroll
+                            for (int s = 0; s < NS; ++s) {
+                                const double ui = u[s * (NI + NB) + a], uj = u[s * (NI + NB) + NI + b];
+                                accA[s][a].x = fma(x.x, uj, accA[s][a].x);   // K~[i,l] += v D[j,k]
+                                accA[s][a].y = fma(x.y, uj, accA[s][a].y);
+                                accB[s][b].x = fma(x.x, ui, accB[s][b].x);   // K~[j,l] += v D[i,k]
+                                accB[s][b].y = fma(x.y, ui, accB[s][b].y);
+                                double &ca = cd[s * (NI + NB) + a], &cb = cd[s * (NI + NB) + NI + b];
+                                ca = fma(x.x, dj[s][b].x, fma(x.y, dj[s][b].y, ca));   // K~[i,k] += v D[j,l]
+                                cb = fma(x.x, di[s][a].x, fma(x.y, di[s][a].y, cb));   // K~[j,k] += v D[i,l]
+                            }
+                        }
+                    }
+                double2 cur = s_jt[kk * 32 + lane];
+                // ---- B: publish the partials of sub-row kk-1 (buffer (kk-1) & 1)
+                if (WANTK) {
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
+                }
+                // ---- C, arithmetic: finish sub-row kk-2
+                double csum[NVP];
+                if (WANTK) {
+#pragma unroll
+                    for (int h = 0; h < NVP; ++h) {
+                        double sum = (r4[h][0] + r4[h][1]) + (r4[h][2] + r4[h][3]);
+                        sum += shfl_xor_f64(sum, 1);
+                        sum += shfl_xor_f64(sum, 2);
+                        csum[h] = sum;
+                    }
+                }
+                // ---- stores last (they may not be reordered above the loads of this iteration).  All of them are
+                // unconditional: after the xor shuffles both half-warps (all four lanes of a quad) hold the same value
+                // and store it to the same address; results that must not land (kk < 2) go to the spare column 16.
+                cur.x += jt2.x;
+                cur.y += jt2.y;
+                s_jt[kk * 32 + lane] = cur;
+                if (WANTK) {
+                    double *wr = s_red + ((kk + 1) & 1) * SM::RED_BUF + (lane & 15);
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
+                    const int kcol = kk >= 2 ? kk - 2 : 16;
+#pragma unroll
+                    for (int h = 0; h < NVP; ++h) {
+                        const int v = (8 * h < NV - 8 ? 8 * h : (NV > 8 ? NV - 8 : 0)) + (lane >> 2);
+                        s_kout[v * JK_RED_STRIDE + kcol] = csum[h];
+                    }
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) cdp[q] = cd[q];
+                }
+            }
+            // ---- drain the reduction pipeline: sub-rows nkk-2 (published, not summed) and nkk-1 (not yet published)
+            if (WANTK) {
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
+                if (lane < 16) {
+                    double *wr = s_red + ((nkk + 1) & 1) * SM::RED_BUF + lane;
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {   // d = 0: sub-row nkk-2 (buffer nkk & 1), d = 1: sub-row nkk-1
+                    const int ks = nkk - 2 + d;
+                    const double *rd = s_red + ((nkk + d) & 1) * SM::RED_BUF + red_rd_off;
+#pragma unroll
+                    for (int h = 0; h < NVP; ++h) {
+                        const int v = 8 * h + (lane >> 2);
+                        double sum = 0.0;
+                        if (v < NV) sum = (rd[8 * h * JK_RED_STRIDE] + rd[8 * h * JK_RED_STRIDE + 1]) +
+                                          (rd[8 * h * JK_RED_STRIDE + 2] + rd[8 * h * JK_RED_STRIDE + 3]);
+                        sum += shfl_xor_f64(sum, 1);
+                        sum += shfl_xor_f64(sum, 2);
+                        if ((lane & 3) == 0 && v < NV && ks >= 0) s_kout[v * JK_RED_STRIDE + ks] = sum;
+                    }
+                }
+                __syncwarp();
+                // reduced K~[row_q, k0 .. k0+nkk) leave with coalesced reds (16 consecutive k per value)
+#pragma unroll
+                for (int m = 0; m < (NV + 1) / 2; ++m) {
+                    const int q = 2 * m + (lane >> 4);
+                    const double v = q < NV ? s_kout[q * JK_RED_STRIDE + (lane & 15)] : 0.0;
+                    flush_add<FIXED>(kout_ok[m], kout_dst[m], v, fx);
+                }
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const bool ok = lane_in && (j0 + b < n);
+                        double *dst = p.kt + s * nl + (size_t)(ok ? j0 + b : 0) * ldd + (ok ? l0 : 0);
+                        flush_add<FIXED>(ok, dst, accB[s][b].x, fx);
+                        flush_add<FIXED>(ok, dst + 1, accB[s][b].y, fx);
+                    }
+            }
+            {
+                // J~[i_a, j_b]: reduce the R row dots across the warp (same shared-memory transpose, 8 per pass)
+#pragma unroll
+                for (int r = 0; r < R; ++r) accJ[r] += shfl_xor_f64(accJ[r], 16);
+#pragma unroll
+                for (int h = 0; h < (R + 7) / 8; ++h) {
+                    __syncwarp();
+                    if (lane < 16) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (8 * h + q < R) s_red[q * JK_RED_STRIDE + lane] = accJ[8 * h + q];
+                    }
+                    __syncwarp();
+                    const int v = 8 * h + (lane >> 2);
+                    const double *rd = s_red + red_rd_off;
+                    double sum = 0.0;
+                    if (v < R) sum = (rd[0] + rd[1]) + (rd[2] + rd[3]);
+                    sum += shfl_xor_f64(sum, 1);
+                    sum += shfl_xor_f64(sum, 2);
+                    const int i = i0 + (v & 3), j = j0 + (v >> 2);
+                    const bool ok = (lane & 3) == 0 && v < R && i >= 0 && j <= i;   // other slots hold zeros
+                    flush_add<FIXED>(ok, p.jt + (ok ? (size_t)i * ldd + j : 0), sum, fx);
+                }
+            }
+        }
+        flushA();
+        __syncwarp();
+        const int imax0 = __shfl_sync(0xffffffffu, my_imax, 0);   // the list is i-descending: longest sweep first
+        if (lane_in) {
+            const int kmax = imax0 + 1 - k0 < JK_KN ? imax0 + 1 - k0 : JK_KN;
+            for (int kk = 0; kk < kmax; ++kk) {
+                const int k = k0 + kk;
+                const double2 cur = s_jt[kk * 32 + lane];
+                flush_add<FIXED>(l0 <= k, p.jt + (size_t)k * ldd + l0, cur.x, fx);
+                flush_add<FIXED>(l0 + 1 <= k, p.jt + (size_t)k * ldd + l0 + 1, cur.y, fx);
+            }
+        }
+        __syncwarp();
+    }
+    if (p.trace && lane == 0) {
+        unsigned long long *tr = p.trace + 3 * (size_t)(blockIdx.x * WARPS + warp);
+        tr[0] = tr_start;
+        tr[1] = globaltimer_ns();
+        tr[2] = tr_tasks;
+    }
+}
+
+}  // namespace sqcc

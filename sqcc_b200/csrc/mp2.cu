@@ -45,7 +45,7 @@ __device__ __forceinline__ void pair_unrank_dev(int64_t ij, int &i, int &j)
 constexpr int SYM_TR = 128, SYM_TC = 32;
 
 __global__ void __launch_bounds__(256) symmetrize_pairs_kernel(const double *__restrict__ P,
-                                                               const int64_t *__restrict__ rowoff, int64_t npair,
+                                                               const int64_t *__restrict__ ibase, int n, int64_t npair,
                                                                double *__restrict__ S)
 {
     __shared__ double tile[SYM_TR][SYM_TC + 1];
@@ -55,7 +55,12 @@ __global__ void __launch_bounds__(256) symmetrize_pairs_kernel(const double *__r
     const int64_t rs = C0 + lane;
     int k = 0, l = 0;
     if (rs < npair) pair_unrank_dev(rs, k, l);
-    const int64_t coloff = subrow_offset(k) + l;
+    // native v2 address (layout.cuh) = tile(i, j) + imax * colA + colB + slot(i, j) * colw + colx: the column part is
+    // computed once per thread, the row part once per row
+    const int cch = l >> 6, cm = k - LAY_CHUNK * cch;
+    const int colw = lay_w(cm), colx = l - LAY_CHUNK * cch;
+    const int64_t colA = (int64_t)LAY_ROWS * 64 * cch;
+    const int64_t colB = LAY_ROWS * (64 * (-(int64_t)23 * cch - 32 * (int64_t)cch * (cch - 1)) + lay_S(cm));
     const double fkl = k == l ? 2.0 : 1.0;          // 1 / degeneracy factors are exact powers of two
     // (i, j) of this warp's first row, then stepped by 8 rows at a time (no sqrt per row)
     int i = 0, j = 0;
@@ -66,7 +71,10 @@ __global__ void __launch_bounds__(256) symmetrize_pairs_kernel(const double *__r
         double v = 0.0;
         if (pq < npair && rs <= pq) {
             const double f = fkl * (i == j ? 2.0 : 1.0) * (rs == pq ? 2.0 : 1.0);
-            v = P[rowoff[pq] + coloff] * f;
+            const int ib = lay_iblock(n, i), ihi = lay_ihi(n, ib), imax = ihi - 1;
+            const int64_t off = ibase[ib] + (int64_t)(j >> 2) * lay_tile_len(imax) + (int64_t)imax * colA + colB +
+                                (int64_t)lay_slot(ihi, i, j) * colw + colx;
+            v = P[off] * f;
             S[pq * npair + rs] = v;
         }
         tile[r][lane] = v;
@@ -102,7 +110,7 @@ int ao2mo(sqcc_ctx *ctx, const double *d_C1, int n1, const double *d_C2, int n2,
     {   // symmetrised pair matrix
         const dim3 sgrid((unsigned)((npair + SYM_TC - 1) / SYM_TC), (unsigned)((npair + SYM_TR - 1) / SYM_TR));
         SQCC_REQUIRE(sgrid.y <= 65535, "pair matrix too large for one launch");
-        symmetrize_pairs_kernel<<<sgrid, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_rowoff, npair, S);
+        symmetrize_pairs_kernel<<<sgrid, 256, 0, ctx->stream>>>(ctx->d_eri, ctx->d_ibase, (int)n, npair, S);
         ctx->launches += 1;
         SQCC_CUDA(cudaGetLastError());
     }
