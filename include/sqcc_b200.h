@@ -193,8 +193,10 @@ int sqcc_scf_update(sqcc_ctx *ctx);
 int sqcc_scf_get(sqcc_ctx *ctx, double *h_D, double *h_Ct, double *h_eps);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
-/* CUDA-event duration (ms) of the last call's dominant kernel(s): slot 0 = J/K kernel, 1 = J/K finalize,
- * 2 = rho, 3 = vxc, 4 = mp2 transforms, 5 = mp2 energy, 6 = SCF update (X^T F X, eigh, density).  Returns the number of slots written. */
+/* CUDA-event duration (ms) of the dominant kernel(s), MEAN over the calls since the previous query (at most the last
+ * 64, so a timed back-to-back loop reports its own in-loop kernel time): slot 0 = J/K kernel, 1 = J/K finalize /
+ * exchange, 2 = rho, 3 = vxc, 4 = mp2 transforms, 5 = mp2 energy, 6 = SCF update (X^T F X, eigh, density); -1 for
+ * slots without a call since the last query.  Returns the number of slots written. */
 int sqcc_get_timings(sqcc_ctx *ctx, double *ms, int n);
 /* Number of library kernels launched since context creation. */
 int64_t sqcc_launch_count(sqcc_ctx *ctx);

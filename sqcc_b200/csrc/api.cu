@@ -35,19 +35,21 @@ int ensure_pin(sqcc_ctx *ctx, size_t bytes)
 int timer_start(sqcc_ctx *ctx, int slot)
 {
     Timer &t = ctx->timers[slot];
-    if (!t.a) {
-        SQCC_CUDA(cudaEventCreate(&t.a));
-        SQCC_CUDA(cudaEventCreate(&t.b));
+    if (!t.a[t.next]) {
+        SQCC_CUDA(cudaEventCreate(&t.a[t.next]));
+        SQCC_CUDA(cudaEventCreate(&t.b[t.next]));
     }
-    SQCC_CUDA(cudaEventRecord(t.a, ctx->stream));
+    SQCC_CUDA(cudaEventRecord(t.a[t.next], ctx->stream));
     return SQCC_OK;
 }
 
 int timer_stop(sqcc_ctx *ctx, int slot)
 {
     Timer &t = ctx->timers[slot];
-    SQCC_CUDA(cudaEventRecord(t.b, ctx->stream));
+    SQCC_CUDA(cudaEventRecord(t.b[t.next], ctx->stream));
     t.used = true;
+    t.next = (t.next + 1) % TIMER_RING;
+    if (t.count < TIMER_RING) ++t.count;
     return SQCC_OK;
 }
 
@@ -148,10 +150,11 @@ int sqcc_ctx_destroy(sqcc_ctx *ctx)
     cudaFree(ctx->d_mp2work);
     cudaFree(ctx->d_mp2out);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-    for (auto &t : ctx->timers) {
-        if (t.a) cudaEventDestroy(t.a);
-        if (t.b) cudaEventDestroy(t.b);
-    }
+    for (auto &t : ctx->timers)
+        for (int e = 0; e < TIMER_RING; ++e) {
+            if (t.a[e]) cudaEventDestroy(t.a[e]);
+            if (t.b[e]) cudaEventDestroy(t.b[e]);
+        }
     delete ctx;
     return SQCC_OK;
 }
@@ -489,11 +492,17 @@ int sqcc_get_timings(sqcc_ctx *ctx, double *ms, int n)
     for (int s = 0; s < m; ++s) {
         ms[s] = -1.0;
         sqcc::Timer &t = ctx->timers[s];
-        if (t.used) {
-            SQCC_CUDA(cudaEventSynchronize(t.b));
-            float f = 0.f;
-            SQCC_CUDA(cudaEventElapsedTime(&f, t.a, t.b));
-            ms[s] = f;
+        if (t.used && t.count > 0) {   // mean over the launches since the last query
+            double sum = 0.0;
+            for (int e = 0; e < t.count; ++e) {
+                const int idx = (t.next - 1 - e + 2 * TIMER_RING) % TIMER_RING;
+                SQCC_CUDA(cudaEventSynchronize(t.b[idx]));
+                float f = 0.f;
+                SQCC_CUDA(cudaEventElapsedTime(&f, t.a[idx], t.b[idx]));
+                sum += f;
+            }
+            ms[s] = sum / t.count;
+            t.count = 0;
         }
     }
     return m;

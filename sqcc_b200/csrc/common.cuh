@@ -84,8 +84,13 @@ struct Comm {
 
 struct ScfState;   // scf.cu
 
+// CUDA-event timer with a small ring of event pairs: back-to-back calls (a benchmark's timed loop) each get their own
+// pair, sqcc_get_timings returns the MEAN over the pairs recorded since the previous query (at most TIMER_RING).
+constexpr int TIMER_RING = 64;
 struct Timer {
-    cudaEvent_t a = nullptr, b = nullptr;
+    cudaEvent_t a[TIMER_RING] = {}, b[TIMER_RING] = {};
+    int next = 0;     // pair the next start() records into
+    int count = 0;    // pairs recorded since the last query (capped at TIMER_RING)
     bool used = false;
 };
 

@@ -250,13 +250,13 @@ int jk_build_schedule(sqcc_ctx *ctx)
     return SQCC_OK;
 }
 
-template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, int PF>
+template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB>
 static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
 {
-    using SM = JKSmem<NB, WANTK ? NSPIN : 1, STAGES>;
+    using SM = JKSmem<NB, WANTK ? NSPIN : 1, STAGES, SLAB>;
     const size_t smem = (size_t)WARPS * SM::WARP_BYTES;
     static_assert((size_t)WARPS * SM::WARP_BYTES <= 232448, "shared memory per CTA");
-    auto kern = jk_stream_kernel<NB, NSPIN, WANTK, WARPS, STAGES, TMA, FIXED, PF>;
+    auto kern = jk_stream_kernel<NB, NSPIN, WANTK, WARPS, STAGES, TMA, FIXED, HINT, SLAB>;
     SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = ctx->sm_count;
     int max_useful = (p.ntasks + WARPS - 1) / WARPS;
@@ -271,12 +271,15 @@ static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
 template <int NB, int NSPIN, bool WANTK, int STAGES>
 static int launch_stream_cfg(sqcc_ctx *ctx, const JKParams &p)
 {
-    // cfg 0: TMA ring (default)   1: cp.async ring for every piece (A/B of the TMA path)   2: TMA + L2 prefetch 2 pieces ahead
-    if (ctx->jk_fixed) return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, true, 0>(ctx, p);
+    // cfg 0: TMA ring, L2 cache-policy hints, J~ slab (default)   1: cp.async ring for every piece (A/B of the TMA path)
+    //     2: no L2 hints   3: no J~ slab, one more ring stage   4: one ring stage less
+    if (ctx->jk_fixed) return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, true, true, true>(ctx, p);
     switch (ctx->jk_cfg) {
-    case 1: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, false, false, 0>(ctx, p);
-    case 2: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, 2>(ctx, p);
-    default: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, 0>(ctx, p);
+    case 1: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, false, false, true, true>(ctx, p);
+    case 2: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, false, true>(ctx, p);
+    case 3: return launch_stream<NB, NSPIN, WANTK, 8, STAGES + 1, true, false, true, false>(ctx, p);
+    case 4: return launch_stream<NB, NSPIN, WANTK, 8, (STAGES > 2 ? STAGES - 1 : 2), true, false, true, true>(ctx, p);
+    default: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, true, true>(ctx, p);
     }
 }
 

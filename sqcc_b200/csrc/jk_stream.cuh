@@ -25,9 +25,29 @@
 namespace sqcc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes)
+// The ERI stream is read exactly once per build: it goes through L2 with the evict-first policy so that it does not push
+// out the density / accumulator matrices every warp keeps coming back to (with the default policy a line lives ~20 us
+// in the 126 MB L2 at 6.5 TB/s -- shorter than the time between two visits of a D2 tile row by the same warp).
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <bool HINT>
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes, uint64_t pol)
+{
+    if (HINT)
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes), "l"(pol)
+                     : "memory");
+    else
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -61,6 +81,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+}
+// 16-byte read-only load that asks L2 to keep the line (density tiles)
+__device__ __forceinline__ double2 ldg2_keep(const double *p, uint64_t pol)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+    return r;
 }
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
 {
@@ -99,7 +132,7 @@ __device__ __forceinline__ void flush_add(bool pred, double *ptr, double v, doub
 
 constexpr int JK_RED_STRIDE = 17;  // value stride of the reduction scratch (odd: conflict-free 4x4 read pattern)
 
-template <int NB, int NS, int STAGES>
+template <int NB, int NS, int STAGES, bool SLAB>
 struct JKSmem {
     static constexpr int R = 4 * NB;
     static constexpr int NV = NS * (4 + NB);          // lane-partial values reduced per sub-row
@@ -107,7 +140,7 @@ struct JKSmem {
     static constexpr int STAGE_BYTES = R * 512;
     static constexpr int RED_BUF = (NV > 8 ? NV : 8) * JK_RED_STRIDE;   // doubles per buffer (>= 8 values: J~ row dots go 8 at a time)
     static constexpr int OFF_SLAB = 0;                                   // double2 [16][32]
-    static constexpr int OFF_RING = OFF_SLAB + JK_KN * 512;              // [STAGES][R][512 B]
+    static constexpr int OFF_RING = OFF_SLAB + (SLAB ? JK_KN * 512 : 0); // [STAGES][R][512 B]
     static constexpr int OFF_U = OFF_RING + STAGES * STAGE_BYTES;        // double [16][NVE]
     static constexpr int OFF_RED = OFF_U + JK_KN * NVE * 8;              // double [2][RED_BUF]
     static constexpr int OFF_KOUT = OFF_RED + 2 * RED_BUF * 8;           // double [NVE][17]
@@ -117,13 +150,15 @@ struct JKSmem {
 };
 
 // NB: rows j per row-block (4: RHF / J-only, 2: UHF).  TMA: full pieces through cp.async.bulk (false: cp.async only).
-// PF: pieces of L2 prefetch distance ahead of the ring (0: none).
-template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, int PF>
+// HINT: L2 cache-policy hints (evict-first on the ERI stream, evict-last on the density tile rows).
+// SLAB: J~[k, l-chunk] accumulates over the row-blocks of a task in a warp-private shared-memory slab (true) or leaves
+// with two red.global per lane per sub-row (false: the 8 KB pay for one more ring stage).
+template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB>
 __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams p)
 {
     constexpr int NI = 4;
     constexpr int NS = WANTK ? NSPIN : 1;
-    using SM = JKSmem<NB, NS, STAGES>;
+    using SM = JKSmem<NB, NS, STAGES, SLAB>;
     constexpr int R = SM::R, NV = SM::NV, NVE = SM::NVE;
     constexpr int NVP = (NV + 7) / 8;
     constexpr uint32_t STAGE_BYTES = SM::STAGE_BYTES;
@@ -141,9 +176,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
     const int n = p.n, ldd = p.ldd;
     const size_t nl = (size_t)n * ldd;
     const double fx = p.fx_scale;
+    const uint64_t pol_stream = HINT ? l2_policy_evict_first() : 0, pol_keep = HINT ? l2_policy_evict_last() : 0;
     uint32_t stage_w = 0, stage_r = 0, phase_bits = 0;   // ring write / read positions and mbarrier parities, persist across tasks
-    unsigned long long tr_start = 0, tr_tasks = 0;
-    if (p.trace) tr_start = globaltimer_ns();
 
     if (TMA) {
         if (lane == 0) {
@@ -167,10 +201,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         const bool lane_in = l0 < ldd;
         const int w = lay_w(k0 - cbase);                 // piece width of this task (uniform: k0, cbase multiples of 16)
         const bool full = TMA && w == JK_CHUNK;
-        ++tr_tasks;
 
+        if (SLAB) {
 #pragma unroll 4
-        for (int kk = 0; kk < JK_KN; ++kk) s_jt[kk * 32 + lane] = make_double2(0.0, 0.0);
+            for (int kk = 0; kk < JK_KN; ++kk) s_jt[kk * 32 + lane] = make_double2(0.0, 0.0);
+        }
 
         // row-block list of the task, one entry per lane (rb_count <= 32)
         long long my_base = 0;
@@ -210,24 +245,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 if (lane == 0) {
                     const uint32_t bar = bar_u32 + 8 * stage_w;
                     mbar_expect_tx(bar, STAGE_BYTES);
-                    bulk_g2s(dst, prod_src, STAGE_BYTES, bar);
-                    if (PF > 0 && prod_left > PF) bulk_prefetch_l2(prod_src + (size_t)PF * (LAY_ROWS * JK_CHUNK * 8), STAGE_BYTES);
+                    if (HINT)
+                        bulk_g2s_hint(dst, prod_src, STAGE_BYTES, bar, pol_stream);
+                    else
+                        bulk_g2s(dst, prod_src, STAGE_BYTES, bar);
                 }
             } else {
                 const char *src = prod_src + 16 * lane;
                 const uint32_t d = dst + 16 * lane;
                 if (w == 64) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) cp_async16_zfill(d + r * 512, src + r * 64 * 8, lane_bytes);
+                    for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 64 * 8, lane_bytes, pol_stream);
                 } else if (w == 48) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) cp_async16_zfill(d + r * 512, src + r * 48 * 8, lane_bytes);
+                    for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 48 * 8, lane_bytes, pol_stream);
                 } else if (w == 32) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) cp_async16_zfill(d + r * 512, src + r * 32 * 8, lane_bytes);
+                    for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 32 * 8, lane_bytes, pol_stream);
                 } else {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) cp_async16_zfill(d + r * 512, src + r * 16 * 8, lane_bytes);
+                    for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 16 * 8, lane_bytes, pol_stream);
                 }
             }
             prod_src += (size_t)LAY_ROWS * 8 * w;
@@ -334,8 +371,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             double cdp[NV];   // lane partials of the previous sub-row, published one iteration later
 #pragma unroll
             for (int q = 0; q < NV; ++q) cdp[q] = 0.0;
+            // density tile row D2[k0 + kk, l-chunk]: loaded TWO sub-rows ahead (an L2 hit queues behind the ERI stream and
+            // takes longer than one iteration under load)
             const double *d2p = p.d2 + (size_t)k0 * ldd + (lane_in ? l0 : 0);
-            double2 d2n = lane_in ? ldg2(d2p) : make_double2(0.0, 0.0);
+            auto load_d2 = [&](const double *q, bool on) {
+                return on ? (HINT ? ldg2_keep(q, pol_keep) : ldg2(q)) : make_double2(0.0, 0.0);
+            };
+            constexpr bool D2_TWO = NB == 4;   // the dual-density pass has no registers to spare: one sub-row ahead
+            double2 d2n = load_d2(d2p, lane_in);
+            double2 d2nn = D2_TWO ? load_d2(d2p + ldd, lane_in && 1 < nkk) : make_double2(0.0, 0.0);
+            if (D2_TWO) d2p += ldd;
 
 #pragma unroll 2
             for (int kk = 0; kk < nkk; ++kk) {
@@ -365,7 +410,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 // ---- A: the FMA block of sub-row kk
                 const double2 d2 = d2n;
                 d2p += ldd;
-                d2n = (lane_in && kk + 1 < nkk) ? ldg2(d2p) : make_double2(0.0, 0.0);
+                if (D2_TWO) {
+                    d2n = d2nn;
+                    d2nn = load_d2(d2p, lane_in && kk + 2 < nkk);
+                } else {
+                    d2n = load_d2(d2p, lane_in && kk + 1 < nkk);
+                }
                 double u[NVE];
                 if (WANTK) {
                     const double2 *up = reinterpret_cast<const double2 *>(s_u + kk * NVE);
@@ -405,7 +455,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                             }
                         }
                     }
-                double2 cur = s_jt[kk * 32 + lane];
+                double2 cur = SLAB ? s_jt[kk * 32 + lane] : make_double2(0.0, 0.0);
                 // ---- B: publish the partials of sub-row kk-1 (buffer (kk-1) & 1)
                 if (WANTK) {
 #pragma unroll
@@ -427,7 +477,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 // and store it to the same address; results that must not land (kk < 2) go to the spare column 16.
                 cur.x += jt2.x;
                 cur.y += jt2.y;
-                s_jt[kk * 32 + lane] = cur;
+                if (SLAB) {
+                    s_jt[kk * 32 + lane] = cur;
+                } else {
+                    // unconditional: cells with l > k hold exact zeros (stored zeros times finite operands); lanes past the
+                    // matrix add their zeros to column 0
+                    double *dst = p.jt + (size_t)(k0 + kk) * ldd + (lane_in ? l0 : 0);
+                    flush_add<FIXED>(true, dst, cur.x, fx);
+                    flush_add<FIXED>(true, dst + 1, cur.y, fx);
+                }
                 if (WANTK) {
                     double *wr = s_red + ((kk + 1) & 1) * SM::RED_BUF + (lane & 15);
 #pragma unroll
@@ -514,7 +572,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         flushA();
         __syncwarp();
         const int imax0 = __shfl_sync(0xffffffffu, my_imax, 0);   // the list is i-descending: longest sweep first
-        if (lane_in) {
+        if (SLAB && lane_in) {
             const int kmax = imax0 + 1 - k0 < JK_KN ? imax0 + 1 - k0 : JK_KN;
             for (int kk = 0; kk < kmax; ++kk) {
                 const int k = k0 + kk;
@@ -524,12 +582,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             }
         }
         __syncwarp();
-    }
-    if (p.trace && lane == 0) {
-        unsigned long long *tr = p.trace + 3 * (size_t)(blockIdx.x * WARPS + warp);
-        tr[0] = tr_start;
-        tr[1] = globaltimer_ns();
-        tr[2] = tr_tasks;
     }
 }
 

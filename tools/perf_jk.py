@@ -23,27 +23,29 @@ eng.attach_eri_synth(n, 20261019)
 eng.synchronize()
 native, algo = eng.eri_bytes()
 print(f"N={n} native {native / 1e9:.2f} GB algorithmic {algo / 1e9:.2f} GB", flush=True)
-for variant in variants:
-    eng.set_jk_variant(variant)
+rounds = int(os.environ.get("PERF_ROUNDS", "3"))
+res = {}
+for rnd in range(rounds):      # variants interleaved: the power controller drifts over seconds
     for tag, dd, wk in (("rhf", d, True), ("uhf", du, True), ("jonly", d, False)):
-        out = torch.empty((1 + (dd.dim() - 1 if wk else 0) * (2 if dd.dim() == 3 else 1) + (0 if not wk or dd.dim() == 3 else 0), n, n),
-                          dtype=torch.float64, device="cuda") if False else None
-        t0 = time.time()
-        reps = 0
-        while time.time() - t0 < 1.2:     # warm-up into the power-capped steady state
-            for _ in range(10):
+        for variant in variants:
+            eng.set_jk_variant(variant)
+            t0 = time.time()
+            while time.time() - t0 < (1.0 if rnd == 0 else 0.3):     # warm-up into the power-capped steady state
+                for _ in range(10):
+                    eng.jk_device(dd, wk)
+                torch.cuda.synchronize()
+            steps = 40
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
                 eng.jk_device(dd, wk)
+            e1.record()
             torch.cuda.synchronize()
-            reps += 10
-        steps = max(10, min(200, reps // 2))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            eng.jk_device(dd, wk)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        kms = eng.timings()["jk_kernel"]
-        print(f"  variant {variant:2d} {tag:5s} step {ms:8.3f} ms  kernel(last) {kms:8.3f} ms  {algo / (ms * 1e-3) / 1e9:7.1f} GB/s algorithmic "
-              f"({native / (ms * 1e-3) / 1e9:7.1f} native)  {1e3 / ms:7.2f} builds/s", flush=True)
+            res.setdefault((tag, variant), []).append(e0.elapsed_time(e1) / steps)
+for tag in ("rhf", "uhf", "jonly"):
+    for variant in variants:
+        ms = res[(tag, variant)]
+        m = float(np.median(ms))
+        print(f"  {tag:5s} variant {variant:2d}  step ms {' '.join(f'{x:7.3f}' for x in ms)}  median {m:7.3f}  "
+              f"{algo / (m * 1e-3) / 1e9:7.1f} GB/s algorithmic ({native / (m * 1e-3) / 1e9:7.1f} native)  {1e3 / m:7.2f} builds/s", flush=True)
 eng.close()
