@@ -64,6 +64,9 @@ int64_t sqcc_nquad(int n);
  * cost; every 4 x 4 row-block of the J/K kernel is whole on exactly one rank. */
 int64_t sqcc_tile_count(int n);
 int sqcc_shard_tiles(int n, int world, int rank, int64_t *t_begin, int64_t *t_end);
+/* Same with unequal shares: rank r gets weights[r] / sum(weights) of the streaming cost (relative speeds of the GPUs:
+ * under their power caps the GPUs of one box sustain different clocks; equal shards leave the fast ones waiting). */
+int sqcc_shard_tiles_weighted(int n, int world, int rank, const double *weights, int64_t *t_begin, int64_t *t_end);
 /* Rows held by the tile range: for every i the interval [jlo[i], jhi[i]) of j (arrays of N ints). */
 int sqcc_tile_rows(int n, int64_t t_begin, int64_t t_end, int *jlo, int *jhi);
 /* Length in doubles of the native-v2 shard holding tiles [t_begin, t_end). */

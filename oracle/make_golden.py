@@ -72,11 +72,35 @@ def kernels():
     np.savez_compressed(os.path.join(OUT, "ref_kernels.npz"), **out)
 
 
-# name -> (builder, basis, functional, charge, multiplicity, treatment, post)
+def h2_stack(nx, ny, nz, bond=0.74, sep=3.0):
+    """nx x ny x nz H2 molecules (bond along z): closed shells with a large gap, converges without damping."""
+    zs, co = [], []
+    for a in range(nx):
+        for b in range(ny):
+            for c in range(nz):
+                zs += [1, 1]
+                co += [[a * sep, b * sep, c * (sep + bond)], [a * sep, b * sep, c * (sep + bond) + bond]]
+    return sgauss.cluster(zs, co)
+
+
+# name -> (builder, basis, functional, charge, multiplicity, treatment, post[, (mm_coords_ang, mm_charges)])
 def _systems():
     r14 = 1.4 * 0.52917721067
     sq = 0.9
+    mm1 = (np.array([[4.0, 0.0, 0.0]]), np.array([-1.1]))          # the point charge of tests/hf_mm/n2_singlet
+    mm2 = (np.array([[4.0, 0.0, 0.0], [0.0, 3.0, 2.0]]), np.array([-1.1, 0.6]))
     return {
+        # QM/MM (hf_ksdft.py:345-358, :408-414; interface_psi4.py:387-403), mirrors tests/hf_mm/*
+        "h6_rhf_mm": (sgauss.h_chain(6), "sto-3g", None, 0, 1, "restricted", (), mm2),
+        "h4sq_rks_mm": (sgauss.cluster([1, 1, 1, 1], [[0, 0, 0], [0, 0, 0.74], [0, 2.5, 0], [0, 2.5, 0.74]]), "dz-s",
+                        "lda", 0, 1, "restricted", (), mm1),
+        "h4_uhf_triplet_mm": (sgauss.h_chain(4), "sto-3g", None, 0, 3, "unrestricted", (), mm1),
+        # 64 - 96 basis functions: the production J/K schedule (several tasks, 4 x 4 row-blocks, full and narrow pieces)
+        # and the generic N > 64 LDA path under the iteration-count gate
+        "h2x16_dz_rhf": (h2_stack(2, 4, 2), "dz-s", None, 0, 1, "restricted", ("mp2",)),
+        "h2x16_dz_rks": (h2_stack(2, 4, 2), "dz-s", "lda", 0, 1, "restricted", ()),
+        "h2x24_dz_rhf": (h2_stack(2, 6, 2), "dz-s", None, 0, 1, "restricted", ()),
+        "h2x20_dz_uks": (h2_stack(2, 5, 2), "dz-s", "lda", 0, 1, "unrestricted", ()),
         "h2_rhf": (sgauss.cluster([1, 1], [[0, 0, 0], [0, 0, r14]]), "sto-3g", None, 0, 1, "restricted", ()),
         "h6_rhf": (sgauss.h_chain(6), "sto-3g", None, 0, 1, "restricted", ("mp2", "cis")),
         "h6_uhf_singlet": (sgauss.h_chain(6), "sto-3g", None, 0, 1, "unrestricted", ()),
@@ -96,23 +120,40 @@ def _systems():
 
 def scf_runs():
     res = {}
-    for name, (mol, basis, func, charge, mult, treat, post) in _systems().items():
-        calc, energies = rl.run_reference_scf(mol, basis, func, charge, mult, treat)
+    import time
+    only = os.environ.get("GOLDEN_ONLY")          # comma-separated names: regenerate just these, keep the others
+    path = os.path.join(OUT, "ref_scf.json")
+    if only and os.path.exists(path):
+        res = json.load(open(path))
+    for name, spec in _systems().items():
+        if only and name not in only.split(","):
+            continue
+        mol, basis, func, charge, mult, treat, post = spec[:7]
+        mm = spec[7] if len(spec) > 7 else None
+        t0 = time.perf_counter()
+        calc, energies = rl.run_reference_scf(mol, basis, func, charge, mult, treat, mm=mm)
         entry = dict(basis=basis, functional=func, charge=charge, multiplicity=mult, treatment=treat,
                      zs=[int(z) for z in mol[1]], coords=np.asarray(mol[2]).tolist(), mol_xyz=mol[0],
                      energies=energies, iterations=len(energies), converged=bool(calc.converged),
-                     scf_energy=float(calc.scf_energy), num_ao=int(calc.num_ao))
+                     scf_energy=float(calc.scf_energy), num_ao=int(calc.num_ao),
+                     # wall time of the unmodified reference's Calculator(...).scf() in the build container (8 vCPU Xeon,
+                     # NumPy 2.3 / OpenBLAS), integrals from the s-Gaussian stub included: bench.py's SCF wall-time leg
+                     reference_scf_seconds=time.perf_counter() - t0)
+        if mm is not None:
+            entry["mm_coords"] = np.asarray(mm[0]).tolist()
+            entry["mm_charges"] = np.asarray(mm[1]).tolist()
         if "mp2" in post:
             entry["mp2_energy"] = float(rl.run_reference_mp2(calc))
         if "cis" in post:
             entry["cis_energies"] = np.asarray(rl.run_reference_cis(calc)).tolist()
         res[name] = entry
         print(name, entry["iterations"], entry["converged"], entry["scf_energy"])
-    with open(os.path.join(OUT, "ref_scf.json"), "w") as f:
+    with open(path, "w") as f:
         json.dump(res, f, indent=1)
 
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    kernels()
+    if not os.environ.get("GOLDEN_ONLY"):
+        kernels()
     scf_runs()

@@ -22,6 +22,7 @@ SIGNATURES = {
     "sqcc_nquad": (c_i64, [c_int]),
     "sqcc_tile_count": (c_i64, [c_int]),
     "sqcc_shard_tiles": (c_int, [c_int, c_int, c_int, c_i64_p, c_i64_p]),
+    "sqcc_shard_tiles_weighted": (c_int, [c_int, c_int, c_int, c_double_p, c_i64_p, c_i64_p]),
     "sqcc_tile_rows": (c_int, [c_int, c_i64, c_i64, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "sqcc_native_len_tiles": (c_i64, [c_int, c_i64, c_i64]),
     "sqcc_native_offset": (c_i64, [c_int, c_i64, c_int, c_int, c_int, c_int]),

@@ -20,11 +20,18 @@ class ShardPlan:
     Rank r holds the tile range [t_begin, t_end); `jlo`/`jhi` give, per i, the interval of j whose rows (i, j)
     it stores (pair-index order inside the shard buffer)."""
 
-    def __init__(self, n, world=1, rank=0):
+    def __init__(self, n, world=1, rank=0, weights=None):
+        """weights: optional relative speeds of the ranks (share of rank r = weights[r] / sum)."""
         lib = _lib.load()
         self.n, self.world, self.rank = int(n), int(world), int(rank)
+        self.weights = None if weights is None else [float(w) for w in weights]
         b, e = ctypes.c_int64(), ctypes.c_int64()
-        _lib.check(lib.sqcc_shard_tiles(self.n, self.world, self.rank, ctypes.byref(b), ctypes.byref(e)))
+        if self.weights is None:
+            _lib.check(lib.sqcc_shard_tiles(self.n, self.world, self.rank, ctypes.byref(b), ctypes.byref(e)))
+        else:
+            assert len(self.weights) == self.world
+            w = (ctypes.c_double * self.world)(*self.weights)
+            _lib.check(lib.sqcc_shard_tiles_weighted(self.n, self.world, self.rank, w, ctypes.byref(b), ctypes.byref(e)))
         self.t_begin, self.t_end = b.value, e.value
         self.native_len = lib.sqcc_native_len_tiles(self.n, self.t_begin, self.t_end)
         if self.native_len < 0:
@@ -51,8 +58,8 @@ class ShardPlan:
         return [tuple(x) for x in segs]
 
     @staticmethod
-    def all_cuts(n, world):
-        return [ShardPlan(n, world, r) for r in range(world)]
+    def all_cuts(n, world, weights=None):
+        return [ShardPlan(n, world, r, weights) for r in range(world)]
 
 
 def reduce_partials(buf, group=None):
@@ -104,6 +111,8 @@ class FockEngine:
         self.plan = None
         self.eri = None
         self._phi = self._w = None
+        self.shard_weights = None    # relative rank speeds of the current shard cut (None: equal shares)
+        self._refill = None          # re-creates the tensor on a new shard cut (rebalance)
         self._use_stream()
 
     def _use_stream(self):
@@ -139,7 +148,7 @@ class FockEngine:
     def _alloc_shard(self, n):
         self._detach_peers()
         self.n = int(n)
-        self.plan = ShardPlan(n, self.world, self.rank)
+        self.plan = ShardPlan(n, self.world, self.rank, self.shard_weights)
         # + 4 KB of slack: the zero-fill cp.async of the lanes past a narrow piece carry (unread) addresses up to 368
         # bytes beyond the last piece
         self.eri = torch.empty(self.plan.native_len + 512, dtype=torch.float64, device=self.device)
@@ -190,6 +199,7 @@ class FockEngine:
         """Counter-based synthetic packed ERI, generated on the device shard by shard."""
         self._alloc_shard(n)
         _lib.check(self.lib.sqcc_eri_synth(self.ctx, ctypes.c_uint64(seed)))
+        self._refill = lambda: self.attach_eri_synth(n, seed)
         return self
 
     def attach_eri_full(self, eri_full):
@@ -199,6 +209,7 @@ class FockEngine:
         assert eri_full.shape == (n, n, n, n)
         self._alloc_shard(n)
         _lib.check(self.lib.sqcc_eri_pack_full_host(self.ctx, eri_full.ctypes.data_as(ctypes.c_void_p)))
+        self._refill = (lambda: self.attach_eri_full(eri_full)) if self.world > 1 else None   # keeps the host tensor alive
         return self
 
     def attach_eri_canonical(self, packed, n, rows_per_chunk=None):
@@ -252,6 +263,40 @@ class FockEngine:
             used += vals.size
         flush()
         return self
+
+    def rebalance(self, steps=24, rounds=2, damping=1.0):
+        """Re-cut the shards from MEASURED kernel times (collective; needs a tensor that can be re-created: synthetic or
+        a host tensor).  Under their 1000 W caps the GPUs of one box sustain different SM clocks (1.27-1.55 ms for equal
+        shards of N = 494 on 8 GPUs), and the exchange waits for the slowest rank: rank r's share becomes proportional to
+        its measured streaming speed (share / kernel time).  Returns the relative speeds used for the final cut."""
+        import torch.distributed as dist
+        if self._group_size() <= 1 or self._refill is None:
+            return self.shard_weights
+        n = self.n
+        rng = np.random.default_rng(5)
+        d = rng.standard_normal((n, n))
+        d = torch.from_numpy(d + d.T).to(self.device)
+        for _ in range(rounds):
+            for _ in range(8):
+                self.jk_device(d, True)
+            torch.cuda.synchronize()
+            self.timings()
+            for _ in range(steps):
+                self.jk_device(d, True)
+            torch.cuda.synchronize()
+            ms = float(self.timings()["jk_kernel"])
+            t = torch.tensor([ms], dtype=torch.float64, device=self.device)
+            allt = [torch.zeros_like(t) for _ in range(self.world)]
+            dist.all_gather(allt, t, group=self.group)
+            ms_r = np.array([float(x[0]) for x in allt])
+            w_old = np.ones(self.world) if self.shard_weights is None else np.asarray(self.shard_weights)
+            speed = w_old / np.maximum(ms_r, 1e-6)     # cost share of the current cut over the time it took
+            speed = speed / speed.mean()
+            if self.shard_weights is not None and damping < 1.0:
+                speed = damping * speed + (1.0 - damping) * np.asarray(self.shard_weights)
+            self.shard_weights = [float(v) for v in speed]
+            self._refill()
+        return self.shard_weights
 
     def eri_bytes(self):
         a, b = ctypes.c_int64(), ctypes.c_int64()

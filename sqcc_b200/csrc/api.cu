@@ -53,16 +53,29 @@ int timer_stop(sqcc_ctx *ctx, int slot)
     return SQCC_OK;
 }
 
-// Tile index at which shard g of `world` starts: equal-COST cut with 4 x 4 tile granularity.  The cost of a tile is its
-// native length times (1 + alpha / (imax + 1)): short rows spend relatively more of their sub-rows on the triangular edge
-// (narrow pieces move fewer bytes per kernel iteration).
+// Tile index at which shard g of `world` starts: equal-COST cut with 4 x 4 tile granularity.  The J/K kernel spends the
+// same time on every piece (one loop iteration: the 12 x 16 DFMAs run on the stored zeros of a narrow piece as well),
+// so the cost of a tile is its number of pieces, sum over chunks c of (imax + 1 - 64 c), plus SQCC_SHARD_ALPHA (default
+// 1) iterations' worth of per-sweep overhead for every 16 sub-rows (row-block prologue / epilogue).
 static double shard_alpha()
 {
     if (const char *e = getenv("SQCC_SHARD_ALPHA")) return atof(e);
-    return 40.0;
+    return 1.0;
 }
 
-static int64_t tile_cut(int n, int world, int g)
+static double tile_cost(int imax, double alpha)
+{
+    double pieces = 0.0, sweeps = 0.0;
+    for (int c = 0; LAY_CHUNK * c <= imax; ++c) {
+        pieces += imax + 1 - LAY_CHUNK * c;
+        sweeps += (imax + 1 - LAY_CHUNK * c + JK_KN - 1) / JK_KN;
+    }
+    return pieces + alpha * sweeps;
+}
+
+// `weights` (optional, [world]): relative speed of the ranks -- rank r gets the share weights[r] / sum(weights) of the
+// streaming cost instead of 1 / world (GPUs of one box settle at different clocks under their power caps).
+static int64_t tile_cut(int n, int world, int g, const double *weights = nullptr)
 {
     const int64_t nt = tile_count(n);
     if (g <= 0) return 0;
@@ -74,10 +87,17 @@ static int64_t tile_cut(int n, int world, int g)
     const double alpha = shard_alpha();
     for (int ib = 0; ib < lay_nblocks(n); ++ib) {
         const int imax = lay_ihi(n, ib) - 1;
-        const double cost = (double)lay_tile_len(imax) * (1.0 + alpha / (imax + 1.0));
+        const double cost = tile_cost(imax, alpha);
         for (int jb = 0; jb < lay_njb(imax); ++jb) cum.push_back(cum.back() + cost);
     }
-    const double target = cum.back() * (double)g / (double)world;
+    double frac = (double)g / (double)world;
+    if (weights) {
+        double tot = 0.0, part = 0.0;
+        for (int r = 0; r < world; ++r) tot += weights[r];
+        for (int r = 0; r < g; ++r) part += weights[r];
+        frac = part / tot;
+    }
+    const double target = cum.back() * frac;
     int64_t lo = 0, hi = nt;
     while (lo < hi) {  // first tile whose start cost >= target
         int64_t mid = (lo + hi) / 2;
@@ -186,6 +206,17 @@ int sqcc_shard_tiles(int n, int world, int rank, int64_t *t_begin, int64_t *t_en
 {
     SQCC_REQUIRE(n > 0 && world > 0 && rank >= 0 && rank < world && t_begin && t_end, "bad shard arguments");
     int64_t a = tile_cut(n, world, rank), b = tile_cut(n, world, rank + 1);
+    if (b < a) b = a;
+    *t_begin = a;
+    *t_end = b;
+    return SQCC_OK;
+}
+
+int sqcc_shard_tiles_weighted(int n, int world, int rank, const double *weights, int64_t *t_begin, int64_t *t_end)
+{
+    SQCC_REQUIRE(n > 0 && world > 0 && rank >= 0 && rank < world && weights && t_begin && t_end, "bad shard arguments");
+    for (int r = 0; r < world; ++r) SQCC_REQUIRE(weights[r] > 0.0 && isfinite(weights[r]), "weights must be positive");
+    int64_t a = tile_cut(n, world, rank, weights), b = tile_cut(n, world, rank + 1, weights);
     if (b < a) b = a;
     *t_begin = a;
     *t_end = b;

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
     using SM = JKSmem<NB, NS, STAGES, SLAB>;
     constexpr int R = SM::R, NV = SM::NV, NVE = SM::NVE;
     constexpr int NVP = (NV + 7) / 8;
+    constexpr bool DEEP = NB == 4;   // reduction pipeline over three iterations (needs NV more live registers) or two
     constexpr uint32_t STAGE_BYTES = SM::STAGE_BYTES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -398,10 +399,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 const double2 *buf = ring + (size_t)stage_r * (R * 32) + lane;
                 stage_r = (stage_r + 1 == STAGES) ? 0 : stage_r + 1;
 
-                // ---- C, loads: partials of sub-row kk-2 (buffer kk & 1); values past NV read a neighbour's (finite) data
+                // ---- C, loads: partials of sub-row kk-2 (buffer kk & 1; kk-1 and buffer (kk-1) & 1 in the shallow pipeline)
                 double r4[NVP][4];
                 if (WANTK) {
-                    const double *rd = s_red + (kk & 1) * SM::RED_BUF + red_rd_off;
+                    const double *rd = s_red + ((DEEP ? kk : kk + 1) & 1) * SM::RED_BUF + red_rd_off;
 #pragma unroll
                     for (int h = 0; h < NVP; ++h)
 #pragma unroll
@@ -456,8 +457,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                         }
                     }
                 double2 cur = SLAB ? s_jt[kk * 32 + lane] : make_double2(0.0, 0.0);
-                // ---- B: publish the partials of sub-row kk-1 (buffer (kk-1) & 1)
+                // ---- B: publish the partials of sub-row kk-1 (buffer (kk-1) & 1); shallow pipeline: of sub-row kk itself
                 if (WANTK) {
+                    if (!DEEP) {
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) cdp[q] = cd[q];
+                    }
 #pragma unroll
                     for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
                 }
@@ -487,32 +492,36 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     flush_add<FIXED>(true, dst + 1, cur.y, fx);
                 }
                 if (WANTK) {
-                    double *wr = s_red + ((kk + 1) & 1) * SM::RED_BUF + (lane & 15);
+                    double *wr = s_red + ((DEEP ? kk + 1 : kk) & 1) * SM::RED_BUF + (lane & 15);
 #pragma unroll
                     for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
-                    const int kcol = kk >= 2 ? kk - 2 : 16;
+                    const int kcol = DEEP ? (kk >= 2 ? kk - 2 : 16) : (kk >= 1 ? kk - 1 : 16);
 #pragma unroll
                     for (int h = 0; h < NVP; ++h) {
                         const int v = (8 * h < NV - 8 ? 8 * h : (NV > 8 ? NV - 8 : 0)) + (lane >> 2);
                         s_kout[v * JK_RED_STRIDE + kcol] = csum[h];
                     }
+                    if (DEEP) {
 #pragma unroll
-                    for (int q = 0; q < NV; ++q) cdp[q] = cd[q];
+                        for (int q = 0; q < NV; ++q) cdp[q] = cd[q];
+                    }
                 }
             }
             // ---- drain the reduction pipeline: sub-rows nkk-2 (published, not summed) and nkk-1 (not yet published)
             if (WANTK) {
                 __syncwarp();
+                if (DEEP) {
 #pragma unroll
-                for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
-                if (lane < 16) {
-                    double *wr = s_red + ((nkk + 1) & 1) * SM::RED_BUF + lane;
+                    for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
+                    if (lane < 16) {
+                        double *wr = s_red + ((nkk + 1) & 1) * SM::RED_BUF + lane;
 #pragma unroll
-                    for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
+                        for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
 #pragma unroll
-                for (int d = 0; d < 2; ++d) {   // d = 0: sub-row nkk-2 (buffer nkk & 1), d = 1: sub-row nkk-1
+                for (int d = DEEP ? 0 : 1; d < 2; ++d) {   // d = 0: sub-row nkk-2 (buffer nkk & 1), d = 1: sub-row nkk-1
                     const int ks = nkk - 2 + d;
                     const double *rd = s_red + ((nkk + d) & 1) * SM::RED_BUF + red_rd_off;
 #pragma unroll

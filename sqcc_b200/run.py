@@ -7,6 +7,8 @@ Reads ./sqc.conf exactly like the reference, runs HF/KS-DFT and, on request, MP2
 this package's scope: requesting them raises a clear error instead of silently skipping work.
 """
 import logging
+
+import numpy as np
 import os
 import sys
 import time
@@ -56,12 +58,23 @@ def run_mp2(scf_object):
 
 
 def run_analysis(scf_object, analysis_params):
-    """Density plots live in the reference's visualizer.py (matplotlib + Psi4): not part of the Fock-build path."""
-    wanted = [k for k in ("electron_density", "electron_density_difference") if analysis_params.get(k)]
-    if wanted:
+    """run.py:137-237.  The numerical part of the density analysis -- rho on the 1000 x 1000 sampling planes,
+    visualizer.py:49-87 -- runs on the device (sqcc_b200/visualizer.py) and is written to density_plane_<axis>.npz;
+    the matplotlib figures themselves (visualizer.py:200-618) and the density-difference mode that re-reads two
+    mo_data.json files are not part of the Fock-build path."""
+    if analysis_params.get("electron_density_difference"):
         raise NotImplementedError(
-            "sqcc_b200 accelerates the SCF/MP2/CIS path only; run the reference visualizer on mo_data.json for: "
-            + ", ".join(wanted))
+            "sqcc_b200 accelerates the SCF/MP2/CIS path and the density sampling only; run the reference visualizer on "
+            "the two mo_data.json files for: electron_density_difference")
+    if analysis_params.get("electron_density") and scf_object is not None:
+        from .visualizer import DensityVisualizer
+
+        def work():
+            vis = DensityVisualizer(scf_object)
+            for axis in "xyz":
+                rho, gu, gv = vis.density_on_plane(axis=axis, num_points=1000)
+                np.savez_compressed(f"density_plane_{axis}.npz", rho=rho, u=gu, v=gv)
+        _timed("run_analysis", work)
 
 
 def main():

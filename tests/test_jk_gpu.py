@@ -213,8 +213,9 @@ def test_direct_block_ingest_equals_full_tensor_pack(n, world):
         a, b = FockEngine(rank=rank, world=world), FockEngine(rank=rank, world=world)
         a.attach_eri_full(full)
         b.attach_eri_blocks(n, blocks(), batch_doubles=4096)     # small batches: several flushes
-        assert a.eri.numel() == b.eri.numel()
-        assert np.array_equal(a.eri.cpu().numpy(), b.eri.cpu().numpy())
+        assert a.plan.native_len == b.plan.native_len     # (the buffers carry a few KB of unread slack behind the shard)
+        m = a.plan.native_len
+        assert np.array_equal(a.eri[:m].cpu().numpy(), b.eri[:m].cpu().numpy())
         a.close()
         b.close()
 

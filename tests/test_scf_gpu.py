@@ -22,8 +22,10 @@ def _run(name, engine, device_scf=False):
     from sqcc_b200 import hf_ksdft
     g = GOLDEN[name]
     hf_ksdft.ipsi4 = sgauss.stub_module()          # same provider surface as interface_psi4, identical integrals
+    mm = (np.array(g["mm_coords"]), np.array(g["mm_charges"])) if "mm_coords" in g else (None, None)
     calc = hf_ksdft.Calculator(g["mol_xyz"], np.array(g["zs"]), np.array(g["coords"]), g["basis"], g["functional"],
-                               g["charge"], g["multiplicity"], g["treatment"], engine=engine, device_scf=device_scf)
+                               g["charge"], g["multiplicity"], g["treatment"], mm[0], mm[1], engine=engine,
+                               device_scf=device_scf)
     out = io.StringIO()
     with contextlib.redirect_stdout(out):
         calc.scf()
@@ -115,3 +117,30 @@ def test_mo_json_roundtrip(engine, tmp_path):
     data = json.load(open(path))
     assert data["calculation_type"] == "unrestricted" and data["num_alpha"] == 3 and data["num_beta"] == 1
     assert len(data["alpha"]["mo_energies"]) == g["num_ao"]
+
+
+def test_density_on_plane_points(engine):
+    """SURVEY.md 8f rank 2 (second half): rho on the 10^6 points of a 1000 x 1000 sampling plane (visualizer.py:202)
+    through the device kernel (sqcc_b200.visualizer.DensityVisualizer.calculate_density_at_points) against the
+    reference's per-point loop form (visualizer.py:82-85) on a sample of the points and its GEMM restatement on all."""
+    from oracle import lda_ref
+    from sqcc_b200.visualizer import DensityVisualizer
+    calc, g, _ = _run("h8_dz_rhf", engine)
+    vis = DensityVisualizer(calc, engine=engine)
+    pts, _ = vis.plane_points(axis="x", offset=0.3, num_points=1000)
+    assert pts.shape == (1_000_000, 3)
+    rho = vis.calculate_density_at_points(pts)
+    phi = calc.psi4_interface.generate_ao_values_at_grids(pts)
+    d = calc.density_matrix_in_ao_basis
+    assert np.abs(rho - lda_ref.rho_gemm(phi, d)).max() <= 1e-11
+    idx = np.random.default_rng(3).integers(0, len(pts), size=2000)
+    assert np.abs(rho[idx] - lda_ref.rho_loop(phi[idx], d)).max() <= 1e-11
+    assert rho.min() >= -1e-14 and rho.max() > 1e-3
+    # unrestricted: total density (visualizer.py:66-71)
+    calc_u, _, _ = _run("h4_uhf_triplet", engine)
+    vis_u = DensityVisualizer(calc_u, engine=engine)
+    p2 = pts[:50000]
+    rho_u = vis_u.calculate_density_at_points(p2)
+    phi_u = calc_u.psi4_interface.generate_ao_values_at_grids(p2)
+    du = calc_u.density_matrix_in_ao_basis
+    assert np.abs(rho_u - lda_ref.rho_gemm(phi_u, du[0] + du[1])).max() <= 1e-11
