@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(256) eri_absmax_kernel(const double *__restric
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
-static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int nb)
+// cw: columns per task chunk (64; 32 for the spin-split UHF pass, whose tasks count 32-column chunks)
+static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int nb, int cw = JK_CHUNK)
 {
     sc.nb = nb;
     sc.h_rowblocks.clear();
@@ -180,7 +181,7 @@ static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int nb)
     // group size: aim for >= ~16 tasks per resident warp, at least 4 and at most 32 row-blocks per task
     int64_t warps = (int64_t)ctx->sm_count * 12;
     int nkr = (ctx->i_end + JK_KN - 1) / JK_KN;
-    int nch = (ctx->i_end + JK_CHUNK - 1) / JK_CHUNK;
+    int nch = (ctx->i_end + cw - 1) / cw;
     int64_t cells = (int64_t)nrb * nkr * (nch + 1) / 2 / 2;  // rough count of (row-block, k-range, chunk) cells
     int group = (int)(cells / (warps * 16));
     if (group < 4) group = 4;
@@ -195,7 +196,7 @@ static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int nb)
     // `tail_waves` tasks per resident warp.
     auto cells_of = [&](int imax) {   // (k-range, chunk) tasks of one row-block: chunks c with 64 c <= k0
         int64_t t = 0;
-        for (int k0 = 0; k0 <= imax; k0 += JK_KN) t += k0 / JK_CHUNK + 1;
+        for (int k0 = 0; k0 <= imax; k0 += JK_KN) t += k0 / cw + 1;
         return t;
     };
     std::vector<int64_t> cells_after(nrb + 1, 0);
@@ -215,7 +216,7 @@ static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int nb)
             int cnt = 0;
             while (g0 + cnt < g1 && sc.h_rowblocks[g0 + cnt].imax >= k0) ++cnt;
             if (cnt == 0) continue;
-            for (int c = 0; c * JK_CHUNK <= k0; ++c) sc.h_tasks.push_back({k0, c, g0, cnt});
+            for (int c = 0; c * cw <= k0; ++c) sc.h_tasks.push_back({k0, c, g0, cnt});
         }
         g0 = g1;
     }
@@ -238,6 +239,7 @@ int jk_build_schedule(sqcc_ctx *ctx)
 {
     SQCC_TRY(build_one_schedule(ctx, ctx->sched[0], 4));
     SQCC_TRY(build_one_schedule(ctx, ctx->sched[1], 2));
+    SQCC_TRY(build_one_schedule(ctx, ctx->sched[2], 4, 32));
     const size_t nl = (size_t)ctx->n * ctx->ldd;
     if (ctx->d_dwork) cudaFree(ctx->d_dwork);
     ctx->d_dwork = nullptr;
@@ -250,13 +252,13 @@ int jk_build_schedule(sqcc_ctx *ctx)
     return SQCC_OK;
 }
 
-template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB>
+template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB, int NH, bool SPIN2 = false>
 static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
 {
-    using SM = JKSmem<NB, WANTK ? NSPIN : 1, STAGES, SLAB>;
+    using SM = JKSmem<NB, (WANTK && !SPIN2) ? NSPIN : 1, STAGES, SLAB, NH, SPIN2>;
     const size_t smem = (size_t)WARPS * SM::WARP_BYTES;
     static_assert((size_t)WARPS * SM::WARP_BYTES <= 232448, "shared memory per CTA");
-    auto kern = jk_stream_kernel<NB, NSPIN, WANTK, WARPS, STAGES, TMA, FIXED, HINT, SLAB>;
+    auto kern = jk_stream_kernel<NB, NSPIN, WANTK, WARPS, STAGES, TMA, FIXED, HINT, SLAB, NH, SPIN2>;
     SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = ctx->sm_count;
     int max_useful = (p.ntasks + WARPS - 1) / WARPS;
@@ -268,18 +270,21 @@ static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
     return SQCC_OK;
 }
 
+// STAGES counts ring slots of whole pieces (R rows).  cfg 4 runs the 4 x 4 shapes with half-piece slots instead (NH = 2:
+// 4 x 4 KB, a slot is handed back as soon as its 8 rows are consumed): more bytes in flight from the same 16 KB, but the
+// second producer / wait step per sub-row costs more than it gains (-12 % RHF, profiles/r02_perf_ab_halfslots.log).
 template <int NB, int NSPIN, bool WANTK, int STAGES>
 static int launch_stream_cfg(sqcc_ctx *ctx, const JKParams &p)
 {
     // cfg 0: TMA ring, L2 cache-policy hints, J~ slab (default)   1: cp.async ring for every piece (A/B of the TMA path)
-    //     2: no L2 hints   3: no J~ slab, one more ring stage   4: one ring stage less
-    if (ctx->jk_fixed) return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, true, true, true>(ctx, p);
+    //     2: no L2 hints   3: no J~ slab, one more ring stage   4: half-piece ring slots (4 x 4 shapes)
+    if (ctx->jk_fixed) return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, true, true, true, 1>(ctx, p);
     switch (ctx->jk_cfg) {
-    case 1: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, false, false, true, true>(ctx, p);
-    case 2: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, false, true>(ctx, p);
-    case 3: return launch_stream<NB, NSPIN, WANTK, 8, STAGES + 1, true, false, true, false>(ctx, p);
-    case 4: return launch_stream<NB, NSPIN, WANTK, 8, (STAGES > 2 ? STAGES - 1 : 2), true, false, true, true>(ctx, p);
-    default: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, true, true>(ctx, p);
+    case 1: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, false, false, true, true, 1>(ctx, p);
+    case 2: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, false, true, 1>(ctx, p);
+    case 3: return launch_stream<NB, NSPIN, WANTK, 8, STAGES + 1, true, false, true, false, 1>(ctx, p);
+    case 4: return launch_stream<NB, NSPIN, WANTK, 8, (NB == 4 ? 2 * STAGES : STAGES), true, false, true, true, (NB == 4 ? 2 : 1)>(ctx, p);
+    default: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, true, true, 1>(ctx, p);
     }
 }
 
@@ -332,7 +337,9 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
     SQCC_CUDA(cudaGetLastError());
 
     const bool uhf = nspin == 2 && want_k;
-    const JKSchedule &sc = ctx->sched[uhf ? 1 : 0];
+    // UHF: jk_cfg 6 = spin-split half-warps over 4 x 4 row-blocks and 32-column chunks (sched[2]); else 4 x 2 row-blocks
+    const bool uhf_split = uhf && ctx->jk_variant == 0 && ctx->jk_cfg == 6 && !ctx->jk_fixed;
+    const JKSchedule &sc = ctx->sched[uhf ? (uhf_split ? 2 : 1) : 0];
     JKParams p;
     p.P = ctx->d_eri;
     p.n = n;
@@ -368,7 +375,9 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
         ctx->launches++;
         SQCC_CUDA(cudaGetLastError());
     } else if (p.ntasks > 0) {
-        if (uhf)
+        if (uhf_split)
+            SQCC_TRY((launch_stream<4, 2, true, 8, 3, false, false, true, true, 1, true>(ctx, p)));
+        else if (uhf)
             SQCC_TRY((launch_stream_cfg<2, 2, true, 3>(ctx, p)));
         else if (!want_k)
             SQCC_TRY((launch_stream_cfg<4, 1, false, 2>(ctx, p)));

@@ -132,19 +132,28 @@ __device__ __forceinline__ void flush_add(bool pred, double *ptr, double v, doub
 
 constexpr int JK_RED_STRIDE = 17;  // value stride of the reduction scratch (odd: conflict-free 4x4 read pattern)
 
-template <int NB, int NS, int STAGES, bool SLAB>
+// NH: ring slots per sub-row.  NH = 2 (4 x 4 row-blocks): a slot holds HALF a piece (8 rows, 4 KB) and is handed back to
+// the producer as soon as its 8 rows are consumed, so the same 16 KB ring keeps up to 3 half-pieces (12 KB instead of 8 KB)
+// in flight -- the per-sub-row time is (latency + compute) / slots until compute bounds it.
+// SPIN2 (dual-density UHF pass): the two half-warps work on the SAME integrals (16 rows x 32 columns, two
+// columns per lane) for the two spin densities, so every per-spin array exists once per lane (NS = 1) and the per-spin
+// shared-memory arrays twice per warp.
+template <int NB, int NS, int STAGES, bool SLAB, int NH, bool SPIN2>
 struct JKSmem {
     static constexpr int R = 4 * NB;
-    static constexpr int NV = NS * (4 + NB);          // lane-partial values reduced per sub-row
+    static constexpr int HR = R / NH;                 // rows per ring slot
+    static constexpr int NV = NS * (4 + NB);          // lane-partial values reduced per sub-row (per half-warp if SPIN2)
     static constexpr int NVE = (NV + 1) & ~1;
-    static constexpr int STAGE_BYTES = R * 512;
-    static constexpr int RED_BUF = (NV > 8 ? NV : 8) * JK_RED_STRIDE;   // doubles per buffer (>= 8 values: J~ row dots go 8 at a time)
-    static constexpr int OFF_SLAB = 0;                                   // double2 [16][32]
-    static constexpr int OFF_RING = OFF_SLAB + (SLAB ? JK_KN * 512 : 0); // [STAGES][R][512 B]
-    static constexpr int OFF_U = OFF_RING + STAGES * STAGE_BYTES;        // double [16][NVE]
-    static constexpr int OFF_RED = OFF_U + JK_KN * NVE * 8;              // double [2][RED_BUF]
-    static constexpr int OFF_KOUT = OFF_RED + 2 * RED_BUF * 8;           // double [NVE][17]
-    static constexpr int OFF_W = OFF_KOUT + NVE * JK_RED_STRIDE * 8;     // double [R]
+    static constexpr int NSP = SPIN2 ? 2 : 1;
+    static constexpr int ROW_BYTES = SPIN2 ? 256 : 512;      // one row of a ring slot / of the J~ slab
+    static constexpr int STAGE_BYTES = HR * ROW_BYTES;
+    static constexpr int RED_BUF = (NSP * NV > 8 ? NSP * NV : 8) * JK_RED_STRIDE;   // doubles per buffer (>= 8 values: J~ row dots go 8 at a time)
+    static constexpr int OFF_SLAB = 0;                                   // double2 [16][32 | 16]
+    static constexpr int OFF_RING = OFF_SLAB + (SLAB ? JK_KN * ROW_BYTES : 0); // [STAGES][HR][ROW_BYTES]
+    static constexpr int OFF_U = OFF_RING + STAGES * STAGE_BYTES;        // double [NSP][16][NVE]
+    static constexpr int OFF_RED = OFF_U + NSP * JK_KN * NVE * 8;        // double [2][RED_BUF]
+    static constexpr int OFF_KOUT = OFF_RED + 2 * RED_BUF * 8;           // double [NSP * NVE][17]
+    static constexpr int OFF_W = OFF_KOUT + NSP * NVE * JK_RED_STRIDE * 8;     // double [R]
     static constexpr int OFF_BAR = OFF_W + R * 8;                        // u64 [STAGES]
     static constexpr int WARP_BYTES = (OFF_BAR + STAGES * 8 + 63) & ~63;
 };
@@ -153,18 +162,26 @@ struct JKSmem {
 // HINT: L2 cache-policy hints (evict-first on the ERI stream, evict-last on the density tile rows).
 // SLAB: J~[k, l-chunk] accumulates over the row-blocks of a task in a warp-private shared-memory slab (true) or leaves
 // with two red.global per lane per sub-row (false: the 8 KB pay for one more ring stage).
-template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB>
+// SPIN2: dual-density pass with the spins on the two half-warps (NB = 4, cp.async ring, 32-column chunks: task.chunk counts
+// 32-column chunks); lane = 16 spin + column pair.
+template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB, int NH, bool SPIN2>
 __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams p)
 {
     constexpr int NI = 4;
-    constexpr int NS = WANTK ? NSPIN : 1;
-    using SM = JKSmem<NB, NS, STAGES, SLAB>;
-    constexpr int R = SM::R, NV = SM::NV, NVE = SM::NVE;
+    constexpr int NS = (WANTK && !SPIN2) ? NSPIN : 1;
+    using SM = JKSmem<NB, NS, STAGES, SLAB, NH, SPIN2>;
+    constexpr int R = SM::R, HR = SM::HR, NV = SM::NV, NVE = SM::NVE;
+    static_assert(NB % NH == 0, "a ring slot holds whole j-columns of the row-block");
+    static_assert(!SPIN2 || (NB == 4 && NH == 1 && !TMA && WANTK && NSPIN == 2), "spin-split pass: 4 x 4 row-blocks, cp.async ring");
+    constexpr int LW = SPIN2 ? 16 : 32;               // double2 per ring-slot row = lanes that share one row
+    constexpr int CW = SPIN2 ? 32 : JK_CHUNK;         // columns per task chunk
     constexpr int NVP = (NV + 7) / 8;
     constexpr bool DEEP = NB == 4;   // reduction pipeline over three iterations (needs NV more live registers) or two
     constexpr uint32_t STAGE_BYTES = SM::STAGE_BYTES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ql = SPIN2 ? (lane & 15) : lane;        // column pair of this lane inside the chunk
+    const int sp = SPIN2 ? (lane >> 4) : 0;           // spin density this lane works for (SPIN2)
     unsigned char *wbase = smem_raw + (size_t)warp * SM::WARP_BYTES;
     double2 *s_jt = reinterpret_cast<double2 *>(wbase + SM::OFF_SLAB);
     const double2 *ring = reinterpret_cast<const double2 *>(wbase + SM::OFF_RING);
@@ -177,6 +194,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
     const int n = p.n, ldd = p.ldd;
     const size_t nl = (size_t)n * ldd;
     const double fx = p.fx_scale;
+    const double *dsp_l = p.dsp + (size_t)sp * nl;    // density / accumulator plane of this lane's spin
+    double *kt_l = p.kt + (size_t)sp * nl;
     const uint64_t pol_stream = HINT ? l2_policy_evict_first() : 0, pol_keep = HINT ? l2_policy_evict_last() : 0;
     uint32_t stage_w = 0, stage_r = 0, phase_bits = 0;   // ring write / read positions and mbarrier parities, persist across tasks
 
@@ -196,16 +215,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= (unsigned)p.ntasks) break;
         const JKTask task = p.tasks[t];
-        const int k0 = task.k0, c = task.chunk;
+        const int k0 = task.k0;
+        const int c = SPIN2 ? task.chunk >> 1 : task.chunk;        // 64-column chunk of the layout
+        const int xcol = (SPIN2 ? (task.chunk & 1) * 32 : 0) + 2 * ql;   // this lane's first column inside the piece
         const int cbase = c * JK_CHUNK;
-        const int l0 = cbase + 2 * lane;
+        const int l0 = cbase + xcol;
         const bool lane_in = l0 < ldd;
         const int w = lay_w(k0 - cbase);                 // piece width of this task (uniform: k0, cbase multiples of 16)
         const bool full = TMA && w == JK_CHUNK;
 
         if (SLAB) {
 #pragma unroll 4
-            for (int kk = 0; kk < JK_KN; ++kk) s_jt[kk * 32 + lane] = make_double2(0.0, 0.0);
+            for (int kk = 0; kk < JK_KN; ++kk) s_jt[kk * LW + ql] = make_double2(0.0, 0.0);
         }
 
         // row-block list of the task, one entry per lane (rb_count <= 32)
@@ -227,9 +248,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         }
 
         // ---- producer: one piece (sub-row) per call
-        int prod_rbi = -1, prod_left = 0, prod_todo = total_it;
+        int prod_rbi = -1, prod_left = 0, prod_todo = total_it * NH, prod_half = 0;   // prod_todo counts ring slots
         const char *prod_src = reinterpret_cast<const char *>(p.P);
-        const uint32_t lane_bytes = 2 * lane < w ? 16u : 0u;
+        const uint32_t lane_bytes = xcol < w ? 16u : 0u;
         auto issue_next = [&]() {
             if (prod_left == 0) {   // next row-block of the list
                 ++prod_rbi;
@@ -242,36 +263,57 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 prod_src = reinterpret_cast<const char *>(p.P + off);
             }
             const uint32_t dst = ring_u32 + stage_w * STAGE_BYTES;
+            const char *half_src = prod_src + (size_t)prod_half * (HR * 8) * w;   // rows [prod_half * HR, +HR) of the piece
             if (full) {
                 if (lane == 0) {
                     const uint32_t bar = bar_u32 + 8 * stage_w;
                     mbar_expect_tx(bar, STAGE_BYTES);
                     if (HINT)
-                        bulk_g2s_hint(dst, prod_src, STAGE_BYTES, bar, pol_stream);
+                        bulk_g2s_hint(dst, half_src, STAGE_BYTES, bar, pol_stream);
                     else
-                        bulk_g2s(dst, prod_src, STAGE_BYTES, bar);
+                        bulk_g2s(dst, half_src, STAGE_BYTES, bar);
+                }
+            } else if (SPIN2) {
+                // 16 rows x 32 columns = 256 16-byte copies: lane (sp, ql) brings the rows of parity sp
+                const char *src = half_src + 8 * xcol + (size_t)sp * 8 * w;
+                const uint32_t d = dst + 16 * ql + 256 * sp;
+                if (w == 64) {
+#pragma unroll
+                    for (int m = 0; m < R / 2; ++m) cp_async16_zfill<HINT>(d + m * 512, src + m * 2 * 64 * 8, lane_bytes, pol_stream);
+                } else if (w == 48) {
+#pragma unroll
+                    for (int m = 0; m < R / 2; ++m) cp_async16_zfill<HINT>(d + m * 512, src + m * 2 * 48 * 8, lane_bytes, pol_stream);
+                } else if (w == 32) {
+#pragma unroll
+                    for (int m = 0; m < R / 2; ++m) cp_async16_zfill<HINT>(d + m * 512, src + m * 2 * 32 * 8, lane_bytes, pol_stream);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < R / 2; ++m) cp_async16_zfill<HINT>(d + m * 512, src + m * 2 * 16 * 8, lane_bytes, pol_stream);
                 }
             } else {
-                const char *src = prod_src + 16 * lane;
+                const char *src = half_src + 16 * lane;
                 const uint32_t d = dst + 16 * lane;
                 if (w == 64) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 64 * 8, lane_bytes, pol_stream);
+                    for (int r = 0; r < HR; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 64 * 8, lane_bytes, pol_stream);
                 } else if (w == 48) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 48 * 8, lane_bytes, pol_stream);
+                    for (int r = 0; r < HR; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 48 * 8, lane_bytes, pol_stream);
                 } else if (w == 32) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 32 * 8, lane_bytes, pol_stream);
+                    for (int r = 0; r < HR; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 32 * 8, lane_bytes, pol_stream);
                 } else {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 16 * 8, lane_bytes, pol_stream);
+                    for (int r = 0; r < HR; ++r) cp_async16_zfill<HINT>(d + r * 512, src + r * 16 * 8, lane_bytes, pol_stream);
                 }
             }
-            prod_src += (size_t)LAY_ROWS * 8 * w;
             stage_w = (stage_w + 1 == STAGES) ? 0 : stage_w + 1;
-            --prod_left;
             --prod_todo;
+            if (++prod_half == NH) {   // piece complete: next sub-row
+                prod_half = 0;
+                prod_src += (size_t)LAY_ROWS * 8 * w;
+                --prod_left;
+            }
         };
 #pragma unroll
         for (int s = 0; s < STAGES - 1; ++s) {
@@ -294,7 +336,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     for (int a = 0; a < NI; ++a) {
                         const int i = cur_i0 + a;
                         const bool ok = lane_in && i >= 0;
-                        double *dst = p.kt + s * nl + (size_t)(ok ? i : 0) * ldd + (ok ? l0 : 0);
+                        double *dst = kt_l + s * nl + (size_t)(ok ? i : 0) * ldd + (ok ? l0 : 0);
                         flush_add<FIXED>(ok, dst, accA[s][a].x, fx);
                         flush_add<FIXED>(ok, dst + 1, accA[s][a].y, fx);
                     }
@@ -303,6 +345,45 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
 
         // reduction helpers (pass h handles values 8h .. 8h+7: value 8h + (lane >> 2), 4 lanes per value, 4 entries each)
         const int red_rd_off = (lane >> 2) * JK_RED_STRIDE + (lane & 3) * 4;
+
+        // Operands of a row-block that come from global memory (an L2 round trip takes 1-2 us under the stream's load): they
+        // are fetched into registers BEFORE the previous row-block's epilogue (drain, flushes) and committed after it.
+        //   nx_dj        D_s[j_b, l0..l0+1]                         (lane operands)
+        //   nx_w         D2[i_a, j_b], r = 4 b + a                  (lane r < R; row indices clamped into range: operands of
+        //   nx_u[q]      D_s[row_q, k0 + lane], q = s*(4+NB) + (a | 4+b)   lanes < 16   rows outside the canonical range
+        //                                                                                only ever meet stored zeros)
+        double2 nx_dj[NS][NB];
+        double nx_w = 0.0, nx_u[NV];
+        auto fetch_rb = [&](int rbi) {
+            const int imax = __shfl_sync(0xffffffffu, my_imax, rbi), j0 = __shfl_sync(0xffffffffu, my_j0, rbi);
+            const int i0 = imax - 3;
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    nx_dj[s][b] = make_double2(0.0, 0.0);
+                    if (WANTK && j0 + b < n && lane_in) nx_dj[s][b] = ldg2(dsp_l + s * nl + (size_t)(j0 + b) * ldd + l0);
+                }
+            {
+                int i = i0 + (lane & 3), j = j0 + ((lane >> 2) & (NB - 1));
+                i = i < 0 ? 0 : i;
+                j = j < n ? j : n - 1;
+                nx_w = __ldg(p.d2 + (size_t)i * ldd + j);
+            }
+            if (WANTK) {
+                // 32-bit indexing: nspin * n * ldd < 2^31 for every supported n
+                const int k = (k0 + (lane & 15)) < n ? (k0 + (lane & 15)) : n - 1;
+                const double *dk = dsp_l + k;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const int s = q / (NI + NB), wq = q % (NI + NB);
+                    int row = wq < NI ? i0 + wq : j0 + (wq - NI);
+                    row = row < 0 ? 0 : (row < n ? row : n - 1);
+                    nx_u[q] = __ldg(dk + (s * n + row) * ldd);
+                }
+            }
+        };
+        fetch_rb(0);
 
         for (int rbi = 0; rbi < task.rb_count; ++rbi) {
             const int imax = __shfl_sync(0xffffffffu, my_imax, rbi), j0 = __shfl_sync(0xffffffffu, my_j0, rbi);
@@ -317,7 +398,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     for (int a = 0; a < NI; ++a) {
                         accA[s][a] = make_double2(0.0, 0.0);
                         if (WANTK)
-                            di[s][a] = (i0 + a >= 0 && lane_in) ? ldg2(p.dsp + s * nl + (size_t)(i0 + a) * ldd + l0)
+                            di[s][a] = (i0 + a >= 0 && lane_in) ? ldg2(dsp_l + s * nl + (size_t)(i0 + a) * ldd + l0)
                                                                  : make_double2(0.0, 0.0);
                     }
             }
@@ -327,45 +408,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     accB[s][b] = make_double2(0.0, 0.0);
-                    dj[s][b] = make_double2(0.0, 0.0);
-                    if (WANTK && j0 + b < n && lane_in) dj[s][b] = ldg2(p.dsp + s * nl + (size_t)(j0 + b) * ldd + l0);
+                    dj[s][b] = nx_dj[s][b];
                 }
             double accJ[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) accJ[r] = 0.0;
-            // stage the warp-uniform operands of this row-block in shared memory (row indices clamped into range: operands of
-            // rows outside the canonical range only ever meet stored zeros):
+            // commit the prefetched warp-uniform operands to shared memory:
             //   s_w[r]      = D2[i_a, j_b], r = 4 b + a
             //   s_u[kk][q]  = D_s[row_q, k0+kk], q = s*(NI+NB) + (a | NI+b)
             __syncwarp();
-            if (lane < R) {
-                int i = i0 + (lane & 3), j = j0 + (lane >> 2);
-                i = i < 0 ? 0 : i;
-                j = j < n ? j : n - 1;
-                s_w[lane] = __ldg(p.d2 + (size_t)i * ldd + j);
-            }
-            if (WANTK && lane < JK_KN) {
-                // 32-bit indexing: nspin * n * ldd < 2^31 for every supported n
-                const int k = (k0 + lane) < n ? (k0 + lane) : n - 1;
-                const double *dk = p.dsp + k;
-                double *su = s_u + lane * NVE;
+            if (lane < R) s_w[lane] = nx_w;
+            if (WANTK && (SPIN2 || lane < JK_KN)) {
+                double *su = s_u + (sp * JK_KN + (lane & 15)) * NVE;
 #pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const int s = q / (NI + NB), wq = q % (NI + NB);
-                    int row = wq < NI ? i0 + wq : j0 + (wq - NI);
-                    row = row < 0 ? 0 : (row < n ? row : n - 1);
-                    su[q] = __ldg(dk + (s * n + row) * ldd);
-                }
+                for (int q = 0; q < NV; ++q) su[q] = nx_u[q];
             }
             // destinations of the reduced K~[row_q, k0 + kk] values: lane = kk + 16 (q & 1), pass m covers q = 2m, 2m+1
-            double *kout_dst[(NV + 1) / 2];
-            bool kout_ok[(NV + 1) / 2];
+            // (SPIN2: 16 values, value V = 8 spin + q, pass m covers V = 2m, 2m+1)
+            constexpr int NKV = SPIN2 ? 16 : NV;
+            double *kout_dst[(NKV + 1) / 2];
+            bool kout_ok[(NKV + 1) / 2];
 #pragma unroll
-            for (int m = 0; m < (NV + 1) / 2; ++m) {
-                const int q = 2 * m + (lane >> 4);
-                const int s = q / (NI + NB), wq = q % (NI + NB);
+            for (int m = 0; m < (NKV + 1) / 2; ++m) {
+                const int qv = 2 * m + (lane >> 4);
+                const int q = SPIN2 ? (qv & 7) : qv;
+                const int s = SPIN2 ? (qv >> 3) : q / (NI + NB), wq = q % (NI + NB);
                 const int row = wq < NI ? i0 + wq : j0 + (wq - NI);
-                kout_ok[m] = WANTK && q < NV && row >= 0 && row < n && (lane & 15) < nkk;
+                kout_ok[m] = WANTK && qv < NKV && row >= 0 && row < n && (lane & 15) < nkk;
                 kout_dst[m] = p.kt + (kout_ok[m] ? s * nl + (size_t)row * ldd + k0 + (lane & 15) : 0);
             }
 
@@ -383,25 +452,37 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             double2 d2nn = D2_TWO ? load_d2(d2p + ldd, lane_in && 1 < nkk) : make_double2(0.0, 0.0);
             if (D2_TWO) d2p += ldd;
 
-#pragma unroll 2
-            for (int kk = 0; kk < nkk; ++kk) {
-                __syncwarp();   // iteration kk-1 is complete in every lane: its ring stage is free, its s_red stores are visible
+            // one ring slot: wait for the previous half-iteration in every lane (its slot is free, its shared-memory stores are
+            // visible), refill the freed slot, wait for the oldest one
+            auto next_slot = [&]() -> const double2 * {
+                __syncwarp();
                 if (prod_todo > 0) issue_next();
                 if (full) {
                     mbar_wait(bar_u32 + 8 * stage_r, (phase_bits >> stage_r) & 1u);
                     phase_bits ^= 1u << stage_r;
                 } else {
                     cp_async_commit();
-                    cp_async_wait<STAGES - 1>();   // this lane's 16 bytes of every row of the oldest stage have landed
+                    cp_async_wait<STAGES - 1>();   // this lane's 16 bytes of every row of the oldest slot have landed
                 }
-                __syncwarp();   // converged from here to the end of the body: no divergent branch below (ptxas can then
+                __syncwarp();   // converged from here to the end of the block: no divergent branch below (ptxas can then
                                 // schedule the shuffles into the DFMA block instead of fencing them with BRA.DIV)
-                const double2 *buf = ring + (size_t)stage_r * (R * 32) + lane;
+                const double2 *buf = ring + (size_t)stage_r * (HR * LW) + ql;
                 stage_r = (stage_r + 1 == STAGES) ? 0 : stage_r + 1;
+                return buf;
+            };
+
+#pragma unroll 2
+            for (int kk = 0; kk < nkk; ++kk) {
+                const double2 *buf = next_slot();
 
                 // ---- C, loads: partials of sub-row kk-2 (buffer kk & 1; kk-1 and buffer (kk-1) & 1 in the shallow pipeline)
-                double r4[NVP][4];
-                if (WANTK) {
+                // (SPIN2: 16 values x 16 entries: value lane >> 1, two lanes per value, 8 entries each)
+                double r4[NVP][4], r8[8];
+                if (WANTK && SPIN2) {
+                    const double *rd = s_red + (kk & 1) * SM::RED_BUF + (lane >> 1) * JK_RED_STRIDE + (lane & 1) * 8;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) r8[e] = rd[e];
+                } else if (WANTK) {
                     const double *rd = s_red + ((DEEP ? kk : kk + 1) & 1) * SM::RED_BUF + red_rd_off;
 #pragma unroll
                     for (int h = 0; h < NVP; ++h)
@@ -419,7 +500,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 }
                 double u[NVE];
                 if (WANTK) {
-                    const double2 *up = reinterpret_cast<const double2 *>(s_u + kk * NVE);
+                    const double2 *up = reinterpret_cast<const double2 *>(s_u + (sp * JK_KN + kk) * NVE);
 #pragma unroll
                     for (int q = 0; q < NVE / 2; ++q) {
                         const double2 t2 = up[q];
@@ -431,44 +512,42 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 double cd[NV];
 #pragma unroll
                 for (int q = 0; q < NV; ++q) cd[q] = 0.0;
+                auto fma_rows = [&](const double2 *bf, int half) {
 #pragma unroll
-                for (int b = 0; b < NB; ++b)
+                    for (int bb = 0; bb < NB / NH; ++bb)
 #pragma unroll
-                    for (int a = 0; a < NI; ++a) {
-                        const int r = 4 * b + a;
-                        const double2 x = buf[r * 32];
-                        accJ[r] = fma(x.x, d2.x, fma(x.y, d2.y, accJ[r]));
-                        const double2 w2 = reinterpret_cast<const double2 *>(s_w)[r >> 1];
-                        const double wij = (r & 1) ? w2.y : w2.x;
-                        jt2.x = fma(x.x, wij, jt2.x);
-                        jt2.y = fma(x.y, wij, jt2.y);
-                        if (WANTK) {
+                        for (int a = 0; a < NI; ++a) {
+                            const int b = half * (NB / NH) + bb;
+                            const int r = 4 * b + a;
+                            const double2 x = bf[(4 * bb + a) * LW];
+                            accJ[r] = fma(x.x, d2.x, fma(x.y, d2.y, accJ[r]));
+                            const double2 w2 = reinterpret_cast<const double2 *>(s_w)[r >> 1];
+                            const double wij = (r & 1) ? w2.y : w2.x;
+                            jt2.x = fma(x.x, wij, jt2.x);
+                            jt2.y = fma(x.y, wij, jt2.y);
+                            if (WANTK) {
 #pragma unroll
-                            for (int s = 0; s < NS; ++s) {
-                                const double ui = u[s * (NI + NB) + a], uj = u[s * (NI + NB) + NI + b];
-                                accA[s][a].x = fma(x.x, uj, accA[s][a].x);   // K~[i,l] += v D[j,k]
-                                accA[s][a].y = fma(x.y, uj, accA[s][a].y);
-                                accB[s][b].x = fma(x.x, ui, accB[s][b].x);   // K~[j,l] += v D[i,k]
-                                accB[s][b].y = fma(x.y, ui, accB[s][b].y);
-                                double &ca = cd[s * (NI + NB) + a], &cb = cd[s * (NI + NB) + NI + b];
-                                ca = fma(x.x, dj[s][b].x, fma(x.y, dj[s][b].y, ca));   // K~[i,k] += v D[j,l]
-                                cb = fma(x.x, di[s][a].x, fma(x.y, di[s][a].y, cb));   // K~[j,k] += v D[i,l]
+                                for (int s = 0; s < NS; ++s) {
+                                    const double ui = u[s * (NI + NB) + a], uj = u[s * (NI + NB) + NI + b];
+                                    accA[s][a].x = fma(x.x, uj, accA[s][a].x);   // K~[i,l] += v D[j,k]
+                                    accA[s][a].y = fma(x.y, uj, accA[s][a].y);
+                                    accB[s][b].x = fma(x.x, ui, accB[s][b].x);   // K~[j,l] += v D[i,k]
+                                    accB[s][b].y = fma(x.y, ui, accB[s][b].y);
+                                    double &ca = cd[s * (NI + NB) + a], &cb = cd[s * (NI + NB) + NI + b];
+                                    ca = fma(x.x, dj[s][b].x, fma(x.y, dj[s][b].y, ca));   // K~[i,k] += v D[j,l]
+                                    cb = fma(x.x, di[s][a].x, fma(x.y, di[s][a].y, cb));   // K~[j,k] += v D[i,l]
+                                }
                             }
                         }
-                    }
-                double2 cur = SLAB ? s_jt[kk * 32 + lane] : make_double2(0.0, 0.0);
-                // ---- B: publish the partials of sub-row kk-1 (buffer (kk-1) & 1); shallow pipeline: of sub-row kk itself
-                if (WANTK) {
-                    if (!DEEP) {
-#pragma unroll
-                        for (int q = 0; q < NV; ++q) cdp[q] = cd[q];
-                    }
-#pragma unroll
-                    for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
-                }
-                // ---- C, arithmetic: finish sub-row kk-2
+                };
+                fma_rows(buf, 0);
+                // ---- C, arithmetic: finish sub-row kk-2 (in the first half's block when the sub-row takes two slots)
                 double csum[NVP];
-                if (WANTK) {
+                if (WANTK && SPIN2) {
+                    double sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+                    sum += shfl_xor_f64(sum, 1);
+                    s_kout[(lane >> 1) * JK_RED_STRIDE + (kk >= 2 ? kk - 2 : 16)] = sum;   // both lanes of the pair: same value
+                } else if (WANTK) {
 #pragma unroll
                     for (int h = 0; h < NVP; ++h) {
                         double sum = (r4[h][0] + r4[h][1]) + (r4[h][2] + r4[h][3]);
@@ -476,14 +555,37 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                         sum += shfl_xor_f64(sum, 2);
                         csum[h] = sum;
                     }
+                    // unconditional stores: all four lanes of a quad hold the same sum and store it to the same address;
+                    // results that must not land (kk < 2) go to the spare column 16
+                    const int kcol = DEEP ? (kk >= 2 ? kk - 2 : 16) : (kk >= 1 ? kk - 1 : 16);
+#pragma unroll
+                    for (int h = 0; h < NVP; ++h) {
+                        const int v = (8 * h < NV - 8 ? 8 * h : (NV > 8 ? NV - 8 : 0)) + (lane >> 2);
+                        s_kout[v * JK_RED_STRIDE + kcol] = csum[h];
+                    }
                 }
-                // ---- stores last (they may not be reordered above the loads of this iteration).  All of them are
-                // unconditional: after the xor shuffles both half-warps (all four lanes of a quad) hold the same value
-                // and store it to the same address; results that must not land (kk < 2) go to the spare column 16.
+                if (NH == 2) {
+                    const double2 *buf1 = next_slot();
+                    fma_rows(buf1, 1);
+                }
+                double2 cur = SLAB ? s_jt[kk * LW + ql] : make_double2(0.0, 0.0);
+                // ---- B: publish the partials of sub-row kk-1 (buffer (kk-1) & 1); shallow pipeline: of sub-row kk itself
+                if (WANTK) {
+                    if (!DEEP) {
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) cdp[q] = cd[q];
+                    }
+                    if (!SPIN2) {   // (SPIN2: the 16 lanes of a half-warp publish their own partials, nothing to fold)
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
+                    }
+                }
+                // ---- stores last (they may not be reordered above the loads of this block).  Unconditional: after the xor
+                // shuffle both half-warps hold the same value and store it to the same address.
                 cur.x += jt2.x;
                 cur.y += jt2.y;
                 if (SLAB) {
-                    s_jt[kk * 32 + lane] = cur;
+                    s_jt[kk * LW + ql] = cur;     // (SPIN2: both half-warps hold the same J~ contributions)
                 } else {
                     // unconditional: cells with l > k hold exact zeros (stored zeros times finite operands); lanes past the
                     // matrix add their zeros to column 0
@@ -492,37 +594,45 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     flush_add<FIXED>(true, dst + 1, cur.y, fx);
                 }
                 if (WANTK) {
-                    double *wr = s_red + ((DEEP ? kk + 1 : kk) & 1) * SM::RED_BUF + (lane & 15);
+                    double *wr = s_red + ((DEEP ? kk + 1 : kk) & 1) * SM::RED_BUF + sp * (NV * JK_RED_STRIDE) + (lane & 15);
 #pragma unroll
                     for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
-                    const int kcol = DEEP ? (kk >= 2 ? kk - 2 : 16) : (kk >= 1 ? kk - 1 : 16);
-#pragma unroll
-                    for (int h = 0; h < NVP; ++h) {
-                        const int v = (8 * h < NV - 8 ? 8 * h : (NV > 8 ? NV - 8 : 0)) + (lane >> 2);
-                        s_kout[v * JK_RED_STRIDE + kcol] = csum[h];
-                    }
                     if (DEEP) {
 #pragma unroll
                         for (int q = 0; q < NV; ++q) cdp[q] = cd[q];
                     }
                 }
             }
+            if (rbi + 1 < task.rb_count) fetch_rb(rbi + 1);   // in flight during the epilogue below
             // ---- drain the reduction pipeline: sub-rows nkk-2 (published, not summed) and nkk-1 (not yet published)
             if (WANTK) {
                 __syncwarp();
                 if (DEEP) {
-#pragma unroll
-                    for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
-                    if (lane < 16) {
-                        double *wr = s_red + ((nkk + 1) & 1) * SM::RED_BUF + lane;
+                    if (SPIN2) {
+                        double *wr = s_red + ((nkk + 1) & 1) * SM::RED_BUF + sp * (NV * JK_RED_STRIDE) + ql;
 #pragma unroll
                         for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
+                        if (lane < 16) {
+                            double *wr = s_red + ((nkk + 1) & 1) * SM::RED_BUF + lane;
+#pragma unroll
+                            for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
+                        }
                     }
                     __syncwarp();
                 }
 #pragma unroll
                 for (int d = DEEP ? 0 : 1; d < 2; ++d) {   // d = 0: sub-row nkk-2 (buffer nkk & 1), d = 1: sub-row nkk-1
                     const int ks = nkk - 2 + d;
+                    if (SPIN2) {
+                        const double *rd = s_red + ((nkk + d) & 1) * SM::RED_BUF + (lane >> 1) * JK_RED_STRIDE + (lane & 1) * 8;
+                        double sum = ((rd[0] + rd[1]) + (rd[2] + rd[3])) + ((rd[4] + rd[5]) + (rd[6] + rd[7]));
+                        sum += shfl_xor_f64(sum, 1);
+                        if ((lane & 1) == 0 && ks >= 0) s_kout[(lane >> 1) * JK_RED_STRIDE + ks] = sum;
+                        continue;
+                    }
                     const double *rd = s_red + ((nkk + d) & 1) * SM::RED_BUF + red_rd_off;
 #pragma unroll
                     for (int h = 0; h < NVP; ++h) {
@@ -538,9 +648,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 __syncwarp();
                 // reduced K~[row_q, k0 .. k0+nkk) leave with coalesced reds (16 consecutive k per value)
 #pragma unroll
-                for (int m = 0; m < (NV + 1) / 2; ++m) {
+                for (int m = 0; m < (NKV + 1) / 2; ++m) {
                     const int q = 2 * m + (lane >> 4);
-                    const double v = q < NV ? s_kout[q * JK_RED_STRIDE + (lane & 15)] : 0.0;
+                    const double v = q < NKV ? s_kout[q * JK_RED_STRIDE + (lane & 15)] : 0.0;
                     flush_add<FIXED>(kout_ok[m], kout_dst[m], v, fx);
                 }
 #pragma unroll
@@ -548,15 +658,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
 #pragma unroll
                     for (int b = 0; b < NB; ++b) {
                         const bool ok = lane_in && (j0 + b < n);
-                        double *dst = p.kt + s * nl + (size_t)(ok ? j0 + b : 0) * ldd + (ok ? l0 : 0);
+                        double *dst = kt_l + s * nl + (size_t)(ok ? j0 + b : 0) * ldd + (ok ? l0 : 0);
                         flush_add<FIXED>(ok, dst, accB[s][b].x, fx);
                         flush_add<FIXED>(ok, dst + 1, accB[s][b].y, fx);
                     }
             }
             {
                 // J~[i_a, j_b]: reduce the R row dots across the warp (same shared-memory transpose, 8 per pass)
+                if (!SPIN2) {   // (SPIN2: both half-warps hold the same row dots over the chunk's 16 column pairs)
 #pragma unroll
-                for (int r = 0; r < R; ++r) accJ[r] += shfl_xor_f64(accJ[r], 16);
+                    for (int r = 0; r < R; ++r) accJ[r] += shfl_xor_f64(accJ[r], 16);
+                }
 #pragma unroll
                 for (int h = 0; h < (R + 7) / 8; ++h) {
                     __syncwarp();
@@ -581,11 +693,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         flushA();
         __syncwarp();
         const int imax0 = __shfl_sync(0xffffffffu, my_imax, 0);   // the list is i-descending: longest sweep first
-        if (SLAB && lane_in) {
+        if (SLAB && lane_in && sp == 0) {
             const int kmax = imax0 + 1 - k0 < JK_KN ? imax0 + 1 - k0 : JK_KN;
             for (int kk = 0; kk < kmax; ++kk) {
                 const int k = k0 + kk;
-                const double2 cur = s_jt[kk * 32 + lane];
+                const double2 cur = s_jt[kk * LW + ql];
                 flush_add<FIXED>(l0 <= k, p.jt + (size_t)k * ldd + l0, cur.x, fx);
                 flush_add<FIXED>(l0 + 1 <= k, p.jt + (size_t)k * ldd + l0 + 1, cur.y, fx);
             }

@@ -24,9 +24,12 @@ eng.synchronize()
 native, algo = eng.eri_bytes()
 print(f"N={n} native {native / 1e9:.2f} GB algorithmic {algo / 1e9:.2f} GB", flush=True)
 rounds = int(os.environ.get("PERF_ROUNDS", "3"))
+kinds = os.environ.get("PERF_KINDS", "rhf,uhf,jonly").split(",")
 res = {}
 for rnd in range(rounds):      # variants interleaved: the power controller drifts over seconds
     for tag, dd, wk in (("rhf", d, True), ("uhf", du, True), ("jonly", d, False)):
+        if tag not in kinds:
+            continue
         for variant in variants:
             eng.set_jk_variant(variant)
             t0 = time.time()
@@ -42,7 +45,7 @@ for rnd in range(rounds):      # variants interleaved: the power controller drif
             e1.record()
             torch.cuda.synchronize()
             res.setdefault((tag, variant), []).append(e0.elapsed_time(e1) / steps)
-for tag in ("rhf", "uhf", "jonly"):
+for tag in kinds:
     for variant in variants:
         ms = res[(tag, variant)]
         m = float(np.median(ms))

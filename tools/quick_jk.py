@@ -19,7 +19,7 @@ for n in sizes:
     packed = cjk.synth_canonical(n, seed)
     d = synth.synth_density_rhf(n, max(1, n // 4), 3)
     du = synth.synth_density_uhf(n, max(1, n // 3), max(1, n // 4), 5)
-    for variant in (1, 0, 17, 18):
+    for variant in [int(v) for v in os.environ.get('QUICK_VARIANTS', '1,0,17,18,22').split(',')]:
         eng.set_jk_variant(variant)
         for tag, dd, wk in (("rhf", d, True), ("uhf", du, True), ("jonly", d, False)):
             t0 = time.time()
