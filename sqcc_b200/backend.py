@@ -137,6 +137,8 @@ class FockEngine:
             self._detach_peers(collective)
             self.lib.sqcc_ctx_destroy(self.ctx)
             self.ctx = None
+            self.eri = self._phi = self._w = None     # give the device memory back now, not at garbage collection
+            self._refill = None                       # (the closure refers back to this engine)
 
     def __del__(self):
         try:
@@ -297,6 +299,55 @@ class FockEngine:
             self.shard_weights = [float(v) for v in speed]
             self._refill()
         return self.shard_weights
+
+    # ------------------------------------------------------------------ on-disk cache of the packed shard
+    ERI_FILE_MAGIC = "sqcc-b200 native-v2 ERI shard"
+
+    def save_eri(self, path):
+        """Write this rank's packed shard (native v2 layout, exactly the bytes the kernels stream) to `path` (+ `.json`
+        header).  One file per rank: a later run of the same (n, world, rank, shard cut) attaches it with attach_eri_file
+        instead of asking the integral provider again (the reference recomputes the N^4 tensor on every run,
+        interface_psi4.py:187-190)."""
+        import json
+        hdr = {"magic": self.ERI_FILE_MAGIC, "n": self.n, "world": self.world, "rank": self.rank,
+               "t_begin": self.plan.t_begin, "t_end": self.plan.t_end, "native_len": self.plan.native_len,
+               "shard_weights": self.shard_weights, "dtype": "<f8"}
+        out = np.lib.format.open_memmap(path, mode="w+", dtype=np.float64, shape=(self.plan.native_len,))
+        chunk = 32 << 20
+        stage = torch.empty(chunk, dtype=torch.float64, pin_memory=True)
+        for lo in range(0, self.plan.native_len, chunk):
+            hi = min(self.plan.native_len, lo + chunk)
+            stage[:hi - lo].copy_(self.eri[lo:hi])
+            torch.cuda.current_stream().synchronize()
+            out[lo:hi] = stage[:hi - lo].numpy()
+        out.flush()
+        del out
+        with open(path + ".json", "w") as f:
+            json.dump(hdr, f)
+
+    def attach_eri_file(self, path):
+        """Attach a shard written by save_eri (same n / world / rank / shard cut): memory-mapped, streamed to the device
+        through a pinned staging buffer."""
+        import json
+        hdr = json.load(open(path + ".json"))
+        if hdr.get("magic") != self.ERI_FILE_MAGIC:
+            raise _lib.SqccError(f"{path}: not a sqcc-b200 packed ERI shard")
+        if (hdr["world"], hdr["rank"]) != (self.world, self.rank):
+            raise _lib.SqccError(f"{path}: written by rank {hdr['rank']} of {hdr['world']}, this engine is rank {self.rank} of {self.world}")
+        self.shard_weights = hdr.get("shard_weights")
+        self._alloc_shard(hdr["n"])
+        if (self.plan.t_begin, self.plan.t_end, self.plan.native_len) != (hdr["t_begin"], hdr["t_end"], hdr["native_len"]):
+            raise _lib.SqccError(f"{path}: shard cut differs from this library's (layout / cost model changed)")
+        src = np.load(path, mmap_mode="r")
+        chunk = 32 << 20
+        stage = torch.empty(chunk, dtype=torch.float64, pin_memory=True)
+        for lo in range(0, self.plan.native_len, chunk):
+            hi = min(self.plan.native_len, lo + chunk)
+            stage[:hi - lo].numpy()[...] = src[lo:hi]
+            self.eri[lo:hi].copy_(stage[:hi - lo], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        self._refill = None
+        return self
 
     def eri_bytes(self):
         a, b = ctypes.c_int64(), ctypes.c_int64()

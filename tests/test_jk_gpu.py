@@ -278,6 +278,59 @@ def test_fused_peer_exchange_single_launch(n, world, uhf):
     grp.close()
 
 
+def test_packed_shard_file_cache(tmp_path):
+    """the packed shard written to disk and attached again gives the same tensor and the same J/K
+    (unsharded and as rank 1 of 3)."""
+    from sqcc_b200.backend import FockEngine
+    n, seed = 45, 8
+    d = synth.synth_density_uhf(n, 11, 9, 2)
+    for rank, world in ((0, 1), (1, 3)):
+        a = FockEngine(rank=rank, world=world)
+        a.attach_eri_synth(n, seed)
+        ref = a.jk_device(__import__("torch").from_numpy(d).to(a.device)).cpu().numpy()
+        path = str(tmp_path / f"eri_{rank}_{world}.npy")
+        a.save_eri(path)
+        b = FockEngine(rank=rank, world=world)
+        b.attach_eri_file(path)
+        m = a.plan.native_len
+        assert np.array_equal(a.eri[:m].cpu().numpy(), b.eri[:m].cpu().numpy())
+        got = b.jk_device(__import__("torch").from_numpy(d).to(b.device)).cpu().numpy()
+        assert np.abs(got - ref).max() <= TOL
+        with pytest.raises(Exception):
+            FockEngine(rank=0, world=2).attach_eri_file(path)
+        a.close()
+        b.close()
+
+
+def test_large_basis_700_sharded_on_one_gpu():
+    """N = 700 (round 1 refused N > 680: 32-bit row offsets): the 250 GB native tensor does not fit one B200, so its four
+    tile-range shards are attached one after the other on the same device and their partial J/K summed -- what four
+    ranks would all-reduce -- then checked on sampled entries against the reference loop nest on the lazily generated
+    synthetic tensor."""
+    import torch
+    from sqcc_b200.backend import FockEngine
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs ~65 GB of device memory")
+    n, seed, world = 700, 20261019, 4
+    d = synth.synth_density_rhf(n, 60, 3)
+    dd = torch.from_numpy(d).cuda()
+    total = torch.zeros((2, n, n), dtype=torch.float64, device="cuda")
+    for rank in range(world):
+        eng = FockEngine(rank=rank, world=world)
+        eng.attach_eri_synth(n, seed)
+        total += eng.jk_device(dd)
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+    res = total.cpu().numpy()
+    rng = np.random.default_rng(1)
+    ent = [(0, 0), (699, 699), (699, 0), (350, 351), (681, 690), (1, 0)] + [(int(a), int(b)) for a, b in rng.integers(0, n, size=(6, 2))]
+    je, ke = cjk.jk_entries(cjk.SRC_SYNTH, None, n, seed, d, ent)
+    for t, (p, q) in enumerate(ent):
+        assert abs(res[0][p, q] - je[t]) <= TOL and abs(res[1][p, q] - ke[t]) <= TOL, (p, q)
+    assert np.abs(res[0] - res[0].T).max() <= TOL and np.abs(res[1] - res[1].T).max() <= TOL
+
+
 def test_anthracene_size_494(engine):
     """configs[4] size: N=494 (59.8 GB of unique integrals).  The full tensor cannot exist on the host, so parity
     is checked on sampled (p,q) entries evaluated with the reference loop nest on the lazily generated synthetic
