@@ -86,7 +86,7 @@ __global__ void jk_prep_kernel(const double *__restrict__ D, int nspin, int n, i
 {
     const size_t nl = (size_t)n * ldd;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx == 0) *counter = 0u;
+    if (idx == 0) counter[0] = counter[1] = 0u;
     double da = 0.0, db = 0.0;
     if (idx < nl) {
         const int r = (int)(idx / ldd), c = (int)(idx % ldd);
@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(256) eri_absmax_kernel(const double *__restric
 
 // ---- host side -----------------------------------------------------------------------------------------
 // cw: columns per task chunk (64; 32 for the spin-split UHF pass, whose tasks count 32-column chunks)
-static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int nb, int cw = JK_CHUNK)
+// part: 0 all tasks, 1 only tasks whose pieces are 48 / 64 columns wide, 2 only the narrow ones (16 / 32 columns: the first
+//       two k-ranges of every chunk column), which the narrow-piece pass runs two sub-rows per iteration
+static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int nb, int cw = JK_CHUNK, int part = 0)
 {
     sc.nb = nb;
     sc.h_rowblocks.clear();
@@ -216,7 +218,10 @@ static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int nb, int cw = JK
             int cnt = 0;
             while (g0 + cnt < g1 && sc.h_rowblocks[g0 + cnt].imax >= k0) ++cnt;
             if (cnt == 0) continue;
-            for (int c = 0; c * cw <= k0; ++c) sc.h_tasks.push_back({k0, c, g0, cnt});
+            for (int c = 0; c * cw <= k0; ++c) {
+                const bool narrow = k0 - c * cw < 32;
+                if (part == 0 || (part == 1 && !narrow) || (part == 2 && narrow)) sc.h_tasks.push_back({k0, c, g0, cnt});
+            }
         }
         g0 = g1;
     }
@@ -240,6 +245,8 @@ int jk_build_schedule(sqcc_ctx *ctx)
     SQCC_TRY(build_one_schedule(ctx, ctx->sched[0], 4));
     SQCC_TRY(build_one_schedule(ctx, ctx->sched[1], 2));
     SQCC_TRY(build_one_schedule(ctx, ctx->sched[2], 4, 32));
+    SQCC_TRY(build_one_schedule(ctx, ctx->sched[3], 4, JK_CHUNK, 1));
+    SQCC_TRY(build_one_schedule(ctx, ctx->sched[4], 4, JK_CHUNK, 2));
     const size_t nl = (size_t)ctx->n * ctx->ldd;
     if (ctx->d_dwork) cudaFree(ctx->d_dwork);
     ctx->d_dwork = nullptr;
@@ -252,13 +259,13 @@ int jk_build_schedule(sqcc_ctx *ctx)
     return SQCC_OK;
 }
 
-template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB, int NH, bool SPIN2 = false>
+template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB, int NH, int HM = 0>
 static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
 {
-    using SM = JKSmem<NB, (WANTK && !SPIN2) ? NSPIN : 1, STAGES, SLAB, NH, SPIN2>;
+    using SM = JKSmem<NB, (WANTK && HM != 1) ? NSPIN : 1, STAGES, SLAB, NH, HM>;
     const size_t smem = (size_t)WARPS * SM::WARP_BYTES;
     static_assert((size_t)WARPS * SM::WARP_BYTES <= 232448, "shared memory per CTA");
-    auto kern = jk_stream_kernel<NB, NSPIN, WANTK, WARPS, STAGES, TMA, FIXED, HINT, SLAB, NH, SPIN2>;
+    auto kern = jk_stream_kernel<NB, NSPIN, WANTK, WARPS, STAGES, TMA, FIXED, HINT, SLAB, NH, HM>;
     SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = ctx->sm_count;
     int max_useful = (p.ntasks + WARPS - 1) / WARPS;
@@ -276,8 +283,9 @@ static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
 template <int NB, int NSPIN, bool WANTK, int STAGES>
 static int launch_stream_cfg(sqcc_ctx *ctx, const JKParams &p)
 {
-    // cfg 0: TMA ring, L2 cache-policy hints, J~ slab (default)   1: cp.async ring for every piece (A/B of the TMA path)
-    //     2: no L2 hints   3: no J~ slab, one more ring stage   4: half-piece ring slots (4 x 4 shapes)
+    // cfg 0: TMA ring, L2 cache-policy hints, J~ slab (default; the 4 x 4 shapes add the narrow-piece pass, see jk_partial)
+    //     1: cp.async ring for every piece (A/B of the TMA path)   2: no L2 hints   3: no J~ slab, one more ring stage
+    //     4: half-piece ring slots (4 x 4 shapes)   6: spin-split UHF   7: one pass over all tasks (no narrow-piece pass)
     if (ctx->jk_fixed) return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, true, true, true, 1>(ctx, p);
     switch (ctx->jk_cfg) {
     case 1: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, false, false, true, true, 1>(ctx, p);
@@ -339,7 +347,10 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
     const bool uhf = nspin == 2 && want_k;
     // UHF: jk_cfg 6 = spin-split half-warps over 4 x 4 row-blocks and 32-column chunks (sched[2]); else 4 x 2 row-blocks
     const bool uhf_split = uhf && ctx->jk_variant == 0 && ctx->jk_cfg == 6 && !ctx->jk_fixed;
-    const JKSchedule &sc = ctx->sched[uhf ? (uhf_split ? 2 : 1) : 0];
+    // 4 x 4 shapes, default configuration: the tasks with 48 / 64-column pieces go through the TMA kernel, the narrow ones
+    // (16 / 32 columns) through the narrow-piece pass (two sub-rows per iteration, one per half-warp)
+    const bool two_pass = !uhf && ctx->jk_variant == 0 && ctx->jk_cfg == 0 && !ctx->jk_fixed;
+    const JKSchedule &sc = ctx->sched[uhf ? (uhf_split ? 2 : 1) : (two_pass ? 3 : 0)];
     JKParams p;
     p.P = ctx->d_eri;
     p.n = n;
@@ -374,11 +385,24 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
             jk_simple_kernel<2, true><<<grid, 256, 0, ctx->stream>>>(p, ctx->d_ibase, ctx->d_tfirst, ctx->t_begin, ctx->t_end, ctx->shard_base);
         ctx->launches++;
         SQCC_CUDA(cudaGetLastError());
-    } else if (p.ntasks > 0) {
+    } else if (p.ntasks > 0 || two_pass) {
+        if (two_pass && ctx->sched[4].n_tasks > 0) {   // narrow pieces first (short tasks; the long ones fill the tail)
+            JKParams pn = p;
+            pn.tasks = ctx->sched[4].d_tasks;
+            pn.rowblocks = ctx->sched[4].d_rowblocks;
+            pn.ntasks = ctx->sched[4].n_tasks;
+            pn.counter = ctx->d_counter + 1;
+            if (!want_k)
+                SQCC_TRY((launch_stream<4, 1, false, 8, 2, false, false, true, true, 1, 2>(ctx, pn)));
+            else
+                SQCC_TRY((launch_stream<4, 1, true, 8, 2, false, false, true, true, 1, 2>(ctx, pn)));
+        }
         if (uhf_split)
-            SQCC_TRY((launch_stream<4, 2, true, 8, 3, false, false, true, true, 1, true>(ctx, p)));
+            SQCC_TRY((launch_stream<4, 2, true, 8, 3, false, false, true, true, 1, 1>(ctx, p)));
         else if (uhf)
             SQCC_TRY((launch_stream_cfg<2, 2, true, 3>(ctx, p)));
+        else if (p.ntasks == 0)
+            ;
         else if (!want_k)
             SQCC_TRY((launch_stream_cfg<4, 1, false, 2>(ctx, p)));
         else

@@ -138,22 +138,27 @@ constexpr int JK_RED_STRIDE = 17;  // value stride of the reduction scratch (odd
 // SPIN2 (dual-density UHF pass): the two half-warps work on the SAME integrals (16 rows x 32 columns, two
 // columns per lane) for the two spin densities, so every per-spin array exists once per lane (NS = 1) and the per-spin
 // shared-memory arrays twice per warp.
-template <int NB, int NS, int STAGES, bool SLAB, int NH, bool SPIN2>
+// KS (HM = 2, narrow pieces of the triangular edge, widths 16 / 32): the two half-warps work on two CONSECUTIVE SUB-ROWS
+// of the same 32 columns, so a loop iteration -- whose cost is its 12 x 16 DFMAs whatever the piece width -- covers two
+// sub-rows instead of one.
+template <int NB, int NS, int STAGES, bool SLAB, int NH, int HM>
 struct JKSmem {
+    static constexpr bool SPIN2 = HM == 1, KS = HM == 2, HALF = HM != 0;
     static constexpr int R = 4 * NB;
     static constexpr int HR = R / NH;                 // rows per ring slot
     static constexpr int NV = NS * (4 + NB);          // lane-partial values reduced per sub-row (per half-warp if SPIN2)
     static constexpr int NVE = (NV + 1) & ~1;
-    static constexpr int NSP = SPIN2 ? 2 : 1;
-    static constexpr int ROW_BYTES = SPIN2 ? 256 : 512;      // one row of a ring slot / of the J~ slab
-    static constexpr int STAGE_BYTES = HR * ROW_BYTES;
-    static constexpr int RED_BUF = (NSP * NV > 8 ? NSP * NV : 8) * JK_RED_STRIDE;   // doubles per buffer (>= 8 values: J~ row dots go 8 at a time)
+    static constexpr int NSP = SPIN2 ? 2 : 1;                // spin planes staged in s_u
+    static constexpr int NRV = HALF ? 2 * NV : NV;           // values reduced per iteration (both half-warps)
+    static constexpr int ROW_BYTES = HALF ? 256 : 512;       // one row of a ring slot / of the J~ slab
+    static constexpr int STAGE_BYTES = (KS ? 2 : 1) * HR * ROW_BYTES;
+    static constexpr int RED_BUF = (NRV > 8 ? NRV : 8) * JK_RED_STRIDE;   // doubles per buffer (>= 8 values: J~ row dots go 8 at a time)
     static constexpr int OFF_SLAB = 0;                                   // double2 [16][32 | 16]
     static constexpr int OFF_RING = OFF_SLAB + (SLAB ? JK_KN * ROW_BYTES : 0); // [STAGES][HR][ROW_BYTES]
     static constexpr int OFF_U = OFF_RING + STAGES * STAGE_BYTES;        // double [NSP][16][NVE]
     static constexpr int OFF_RED = OFF_U + NSP * JK_KN * NVE * 8;        // double [2][RED_BUF]
-    static constexpr int OFF_KOUT = OFF_RED + 2 * RED_BUF * 8;           // double [NSP * NVE][17]
-    static constexpr int OFF_W = OFF_KOUT + NSP * NVE * JK_RED_STRIDE * 8;     // double [R]
+    static constexpr int OFF_KOUT = OFF_RED + 2 * RED_BUF * 8;           // double [NRV][17]
+    static constexpr int OFF_W = OFF_KOUT + ((NRV + 1) & ~1) * JK_RED_STRIDE * 8;     // double [R]
     static constexpr int OFF_BAR = OFF_W + R * 8;                        // u64 [STAGES]
     static constexpr int WARP_BYTES = (OFF_BAR + STAGES * 8 + 63) & ~63;
 };
@@ -164,24 +169,28 @@ struct JKSmem {
 // with two red.global per lane per sub-row (false: the 8 KB pay for one more ring stage).
 // SPIN2: dual-density pass with the spins on the two half-warps (NB = 4, cp.async ring, 32-column chunks: task.chunk counts
 // 32-column chunks); lane = 16 spin + column pair.
-template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB, int NH, bool SPIN2>
+// HM = 2 (KS): narrow-piece pass (tasks whose pieces are 16 or 32 columns wide), half-warp = sub-row parity.
+template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB, int NH, int HM>
 __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams p)
 {
     constexpr int NI = 4;
+    constexpr bool SPIN2 = HM == 1, KS = HM == 2, HALF = HM != 0;
     constexpr int NS = (WANTK && !SPIN2) ? NSPIN : 1;
-    using SM = JKSmem<NB, NS, STAGES, SLAB, NH, SPIN2>;
+    using SM = JKSmem<NB, NS, STAGES, SLAB, NH, HM>;
     constexpr int R = SM::R, HR = SM::HR, NV = SM::NV, NVE = SM::NVE;
     static_assert(NB % NH == 0, "a ring slot holds whole j-columns of the row-block");
     static_assert(!SPIN2 || (NB == 4 && NH == 1 && !TMA && WANTK && NSPIN == 2), "spin-split pass: 4 x 4 row-blocks, cp.async ring");
-    constexpr int LW = SPIN2 ? 16 : 32;               // double2 per ring-slot row = lanes that share one row
-    constexpr int CW = SPIN2 ? 32 : JK_CHUNK;         // columns per task chunk
+    static_assert(!KS || (NB == 4 && NH == 1 && !TMA && NS == 1), "narrow-piece pass: 4 x 4 row-blocks, cp.async ring, one density");
+    constexpr int LW = HALF ? 16 : 32;                // double2 per ring-slot row = lanes that share one row
+    constexpr int KSTEP = KS ? 2 : 1;                 // sub-rows per loop iteration
     constexpr int NVP = (NV + 7) / 8;
     constexpr bool DEEP = NB == 4;   // reduction pipeline over three iterations (needs NV more live registers) or two
     constexpr uint32_t STAGE_BYTES = SM::STAGE_BYTES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ql = SPIN2 ? (lane & 15) : lane;        // column pair of this lane inside the chunk
-    const int sp = SPIN2 ? (lane >> 4) : 0;           // spin density this lane works for (SPIN2)
+    const int ql = HALF ? (lane & 15) : lane;         // column pair of this lane inside the chunk
+    const int hh = HALF ? (lane >> 4) : 0;            // half-warp: spin density (SPIN2) / sub-row parity (KS)
+    const int sp = SPIN2 ? hh : 0;                    // spin density this lane works for
     unsigned char *wbase = smem_raw + (size_t)warp * SM::WARP_BYTES;
     double2 *s_jt = reinterpret_cast<double2 *>(wbase + SM::OFF_SLAB);
     const double2 *ring = reinterpret_cast<const double2 *>(wbase + SM::OFF_RING);
@@ -242,6 +251,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         int total_it = 0;
         {
             int cnt = lane < task.rb_count ? (my_imax + 1 - k0 < JK_KN ? my_imax + 1 - k0 : JK_KN) : 0;
+            if (KS) cnt = (cnt + 1) >> 1;   // two sub-rows per iteration
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
             total_it = cnt;
@@ -272,6 +282,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                         bulk_g2s_hint(dst, half_src, STAGE_BYTES, bar, pol_stream);
                     else
                         bulk_g2s(dst, half_src, STAGE_BYTES, bar);
+                }
+            } else if (KS) {
+                // two consecutive narrow pieces, one per half-warp: lane (hh, ql) brings its own 16 bytes of the 16 rows of
+                // sub-row 2 it + hh (zero-filled past the piece width and past the last sub-row of the sweep)
+                const uint32_t nb = (xcol < w && hh < prod_left) ? 16u : 0u;
+                const char *src = half_src + 16 * ql + (size_t)(hh < prod_left ? hh : 0) * (LAY_ROWS * 8) * w;
+                const uint32_t d = dst + 16 * ql + hh * (LAY_ROWS * 256);
+                if (w == 32) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 256, src + r * 32 * 8, nb, pol_stream);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 256, src + r * 16 * 8, nb, pol_stream);
                 }
             } else if (SPIN2) {
                 // 16 rows x 32 columns = 256 16-byte copies: lane (sp, ql) brings the rows of parity sp
@@ -309,10 +332,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             }
             stage_w = (stage_w + 1 == STAGES) ? 0 : stage_w + 1;
             --prod_todo;
-            if (++prod_half == NH) {   // piece complete: next sub-row
+            if (++prod_half == NH) {   // piece complete: next sub-row (KS: next two)
                 prod_half = 0;
-                prod_src += (size_t)LAY_ROWS * 8 * w;
-                --prod_left;
+                prod_src += (size_t)KSTEP * LAY_ROWS * 8 * w;
+                prod_left -= prod_left < KSTEP ? prod_left : KSTEP;
             }
         };
 #pragma unroll
@@ -418,24 +441,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             //   s_u[kk][q]  = D_s[row_q, k0+kk], q = s*(NI+NB) + (a | NI+b)
             __syncwarp();
             if (lane < R) s_w[lane] = nx_w;
-            if (WANTK && (SPIN2 || lane < JK_KN)) {
+            if (WANTK && (SPIN2 || lane < JK_KN)) {   // (KS: one density, rows kk = 0..15 staged by the first half-warp)
                 double *su = s_u + (sp * JK_KN + (lane & 15)) * NVE;
 #pragma unroll
                 for (int q = 0; q < NV; ++q) su[q] = nx_u[q];
             }
             // destinations of the reduced K~[row_q, k0 + kk] values: lane = kk + 16 (q & 1), pass m covers q = 2m, 2m+1
-            // (SPIN2: 16 values, value V = 8 spin + q, pass m covers V = 2m, 2m+1)
-            constexpr int NKV = SPIN2 ? 16 : NV;
-            double *kout_dst[(NKV + 1) / 2];
-            bool kout_ok[(NKV + 1) / 2];
+            // (SPIN2: 16 values, value V = 8 spin + q, pass m covers V = 2m, 2m+1.  KS: 16 values V = 8 parity + q in 8
+            //  iteration columns: lane = it + 8 (V & 3), pass m covers V = 4m .. 4m+3, sub-row kk = 2 it + (V >> 3))
+            constexpr int NKV = HALF ? 16 : NV;
+            constexpr int NKP = KS ? 4 : (NKV + 1) / 2;
+            double *kout_dst[NKP];
+            bool kout_ok[NKP];
 #pragma unroll
-            for (int m = 0; m < (NKV + 1) / 2; ++m) {
-                const int qv = 2 * m + (lane >> 4);
-                const int q = SPIN2 ? (qv & 7) : qv;
-                const int s = SPIN2 ? (qv >> 3) : q / (NI + NB), wq = q % (NI + NB);
+            for (int m = 0; m < NKP; ++m) {
+                const int qv = KS ? 4 * m + (lane >> 3) : 2 * m + (lane >> 4);
+                const int q = HALF ? (qv & 7) : qv;
+                const int s = SPIN2 ? (qv >> 3) : (KS ? 0 : q / (NI + NB)), wq = q % (NI + NB);
                 const int row = wq < NI ? i0 + wq : j0 + (wq - NI);
-                kout_ok[m] = WANTK && qv < NKV && row >= 0 && row < n && (lane & 15) < nkk;
-                kout_dst[m] = p.kt + (kout_ok[m] ? s * nl + (size_t)row * ldd + k0 + (lane & 15) : 0);
+                const int kkq = KS ? 2 * (lane & 7) + (qv >> 3) : (lane & 15);
+                kout_ok[m] = WANTK && qv < NKV && row >= 0 && row < n && kkq < nkk;
+                kout_dst[m] = p.kt + (kout_ok[m] ? s * nl + (size_t)row * ldd + k0 + kkq : 0);
             }
 
             double cdp[NV];   // lane partials of the previous sub-row, published one iteration later
@@ -443,14 +469,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             for (int q = 0; q < NV; ++q) cdp[q] = 0.0;
             // density tile row D2[k0 + kk, l-chunk]: loaded TWO sub-rows ahead (an L2 hit queues behind the ERI stream and
             // takes longer than one iteration under load)
-            const double *d2p = p.d2 + (size_t)k0 * ldd + (lane_in ? l0 : 0);
+            const int hoff = KS ? hh : 0;                      // sub-row of this lane inside an iteration
+            const int nit = KS ? (nkk + 1) >> 1 : nkk;         // loop iterations of this sweep
+            const double *d2p = p.d2 + (size_t)(k0 + hoff) * ldd + (lane_in ? l0 : 0);
             auto load_d2 = [&](const double *q, bool on) {
                 return on ? (HINT ? ldg2_keep(q, pol_keep) : ldg2(q)) : make_double2(0.0, 0.0);
             };
             constexpr bool D2_TWO = NB == 4;   // the dual-density pass has no registers to spare: one sub-row ahead
-            double2 d2n = load_d2(d2p, lane_in);
-            double2 d2nn = D2_TWO ? load_d2(d2p + ldd, lane_in && 1 < nkk) : make_double2(0.0, 0.0);
-            if (D2_TWO) d2p += ldd;
+            double2 d2n = load_d2(d2p, lane_in && hoff < nkk);
+            double2 d2nn = D2_TWO ? load_d2(d2p + KSTEP * ldd, lane_in && KSTEP + hoff < nkk) : make_double2(0.0, 0.0);
+            if (D2_TWO) d2p += KSTEP * ldd;
 
             // one ring slot: wait for the previous half-iteration in every lane (its slot is free, its shared-memory stores are
             // visible), refill the freed slot, wait for the oldest one
@@ -466,19 +494,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 }
                 __syncwarp();   // converged from here to the end of the block: no divergent branch below (ptxas can then
                                 // schedule the shuffles into the DFMA block instead of fencing them with BRA.DIV)
-                const double2 *buf = ring + (size_t)stage_r * (HR * LW) + ql;
+                const double2 *buf = ring + (size_t)stage_r * (STAGE_BYTES / 16) + (KS ? hh * (LAY_ROWS * LW) : 0) + ql;
                 stage_r = (stage_r + 1 == STAGES) ? 0 : stage_r + 1;
                 return buf;
             };
 
 #pragma unroll 2
-            for (int kk = 0; kk < nkk; ++kk) {
+            for (int kk = 0; kk < nit; ++kk) {   // (KS: kk counts iterations of two sub-rows, this lane's is kl)
                 const double2 *buf = next_slot();
+                const int kl = KS ? ((2 * kk + hh) < JK_KN ? 2 * kk + hh : JK_KN - 1) : kk;
 
                 // ---- C, loads: partials of sub-row kk-2 (buffer kk & 1; kk-1 and buffer (kk-1) & 1 in the shallow pipeline)
                 // (SPIN2: 16 values x 16 entries: value lane >> 1, two lanes per value, 8 entries each)
                 double r4[NVP][4], r8[8];
-                if (WANTK && SPIN2) {
+                if (WANTK && HALF) {
                     const double *rd = s_red + (kk & 1) * SM::RED_BUF + (lane >> 1) * JK_RED_STRIDE + (lane & 1) * 8;
 #pragma unroll
                     for (int e = 0; e < 8; ++e) r8[e] = rd[e];
@@ -491,16 +520,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 }
                 // ---- A: the FMA block of sub-row kk
                 const double2 d2 = d2n;
-                d2p += ldd;
+                d2p += KSTEP * ldd;
                 if (D2_TWO) {
                     d2n = d2nn;
-                    d2nn = load_d2(d2p, lane_in && kk + 2 < nkk);
+                    d2nn = load_d2(d2p, lane_in && KSTEP * (kk + 2) + hoff < nkk);
                 } else {
                     d2n = load_d2(d2p, lane_in && kk + 1 < nkk);
                 }
                 double u[NVE];
                 if (WANTK) {
-                    const double2 *up = reinterpret_cast<const double2 *>(s_u + (sp * JK_KN + kk) * NVE);
+                    const double2 *up = reinterpret_cast<const double2 *>(s_u + (sp * JK_KN + kl) * NVE);
 #pragma unroll
                     for (int q = 0; q < NVE / 2; ++q) {
                         const double2 t2 = up[q];
@@ -543,7 +572,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 fma_rows(buf, 0);
                 // ---- C, arithmetic: finish sub-row kk-2 (in the first half's block when the sub-row takes two slots)
                 double csum[NVP];
-                if (WANTK && SPIN2) {
+                if (WANTK && HALF) {
                     double sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
                     sum += shfl_xor_f64(sum, 1);
                     s_kout[(lane >> 1) * JK_RED_STRIDE + (kk >= 2 ? kk - 2 : 16)] = sum;   // both lanes of the pair: same value
@@ -568,14 +597,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     const double2 *buf1 = next_slot();
                     fma_rows(buf1, 1);
                 }
-                double2 cur = SLAB ? s_jt[kk * LW + ql] : make_double2(0.0, 0.0);
+                double2 cur = SLAB ? s_jt[kl * LW + ql] : make_double2(0.0, 0.0);
                 // ---- B: publish the partials of sub-row kk-1 (buffer (kk-1) & 1); shallow pipeline: of sub-row kk itself
                 if (WANTK) {
                     if (!DEEP) {
 #pragma unroll
                         for (int q = 0; q < NV; ++q) cdp[q] = cd[q];
                     }
-                    if (!SPIN2) {   // (SPIN2: the 16 lanes of a half-warp publish their own partials, nothing to fold)
+                    if (!HALF) {   // (half-warp modes: the 16 lanes of a half-warp publish their own partials, nothing to fold)
 #pragma unroll
                         for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
                     }
@@ -585,16 +614,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 cur.x += jt2.x;
                 cur.y += jt2.y;
                 if (SLAB) {
-                    s_jt[kk * LW + ql] = cur;     // (SPIN2: both half-warps hold the same J~ contributions)
+                    s_jt[kl * LW + ql] = cur;     // (SPIN2: both half-warps hold the same J~ contributions; KS: own rows)
                 } else {
                     // unconditional: cells with l > k hold exact zeros (stored zeros times finite operands); lanes past the
                     // matrix add their zeros to column 0
-                    double *dst = p.jt + (size_t)(k0 + kk) * ldd + (lane_in ? l0 : 0);
+                    double *dst = p.jt + (size_t)(k0 + kl) * ldd + (lane_in ? l0 : 0);
                     flush_add<FIXED>(true, dst, cur.x, fx);
                     flush_add<FIXED>(true, dst + 1, cur.y, fx);
                 }
                 if (WANTK) {
-                    double *wr = s_red + ((DEEP ? kk + 1 : kk) & 1) * SM::RED_BUF + sp * (NV * JK_RED_STRIDE) + (lane & 15);
+                    double *wr = s_red + ((DEEP ? kk + 1 : kk) & 1) * SM::RED_BUF + hh * (NV * JK_RED_STRIDE) + (lane & 15);
 #pragma unroll
                     for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
                     if (DEEP) {
@@ -608,15 +637,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             if (WANTK) {
                 __syncwarp();
                 if (DEEP) {
-                    if (SPIN2) {
-                        double *wr = s_red + ((nkk + 1) & 1) * SM::RED_BUF + sp * (NV * JK_RED_STRIDE) + ql;
+                    if (HALF) {
+                        double *wr = s_red + ((nit + 1) & 1) * SM::RED_BUF + hh * (NV * JK_RED_STRIDE) + ql;
 #pragma unroll
                         for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
                     } else {
 #pragma unroll
                         for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
                         if (lane < 16) {
-                            double *wr = s_red + ((nkk + 1) & 1) * SM::RED_BUF + lane;
+                            double *wr = s_red + ((nit + 1) & 1) * SM::RED_BUF + lane;
 #pragma unroll
                             for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
                         }
@@ -624,16 +653,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     __syncwarp();
                 }
 #pragma unroll
-                for (int d = DEEP ? 0 : 1; d < 2; ++d) {   // d = 0: sub-row nkk-2 (buffer nkk & 1), d = 1: sub-row nkk-1
-                    const int ks = nkk - 2 + d;
-                    if (SPIN2) {
-                        const double *rd = s_red + ((nkk + d) & 1) * SM::RED_BUF + (lane >> 1) * JK_RED_STRIDE + (lane & 1) * 8;
+                for (int d = DEEP ? 0 : 1; d < 2; ++d) {   // d = 0: iteration nit-2 (buffer nit & 1), d = 1: iteration nit-1
+                    const int ks = nit - 2 + d;
+                    if (HALF) {
+                        const double *rd = s_red + ((nit + d) & 1) * SM::RED_BUF + (lane >> 1) * JK_RED_STRIDE + (lane & 1) * 8;
                         double sum = ((rd[0] + rd[1]) + (rd[2] + rd[3])) + ((rd[4] + rd[5]) + (rd[6] + rd[7]));
                         sum += shfl_xor_f64(sum, 1);
                         if ((lane & 1) == 0 && ks >= 0) s_kout[(lane >> 1) * JK_RED_STRIDE + ks] = sum;
                         continue;
                     }
-                    const double *rd = s_red + ((nkk + d) & 1) * SM::RED_BUF + red_rd_off;
+                    const double *rd = s_red + ((nit + d) & 1) * SM::RED_BUF + red_rd_off;
 #pragma unroll
                     for (int h = 0; h < NVP; ++h) {
                         const int v = 8 * h + (lane >> 2);
@@ -648,9 +677,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 __syncwarp();
                 // reduced K~[row_q, k0 .. k0+nkk) leave with coalesced reds (16 consecutive k per value)
 #pragma unroll
-                for (int m = 0; m < (NKV + 1) / 2; ++m) {
-                    const int q = 2 * m + (lane >> 4);
-                    const double v = q < NKV ? s_kout[q * JK_RED_STRIDE + (lane & 15)] : 0.0;
+                for (int m = 0; m < NKP; ++m) {
+                    const int q = KS ? 4 * m + (lane >> 3) : 2 * m + (lane >> 4);
+                    const double v = q < NKV ? s_kout[q * JK_RED_STRIDE + (KS ? (lane & 7) : (lane & 15))] : 0.0;
                     flush_add<FIXED>(kout_ok[m], kout_dst[m], v, fx);
                 }
 #pragma unroll
@@ -695,7 +724,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         const int imax0 = __shfl_sync(0xffffffffu, my_imax, 0);   // the list is i-descending: longest sweep first
         if (SLAB && lane_in && sp == 0) {
             const int kmax = imax0 + 1 - k0 < JK_KN ? imax0 + 1 - k0 : JK_KN;
-            for (int kk = 0; kk < kmax; ++kk) {
+            for (int kk = KS ? hh : 0; kk < kmax; kk += KSTEP) {   // (KS: the half-warp that owns the row's parity)
                 const int k = k0 + kk;
                 const double2 cur = s_jt[kk * LW + ql];
                 flush_add<FIXED>(l0 <= k, p.jt + (size_t)k * ldd + l0, cur.x, fx);

@@ -22,7 +22,7 @@ for n in (5, 37, 70):
     j, k = eng.jk(d)
     ju, ku = eng.jk(np.stack([0.5 * d, 0.5 * d]))
     jo, _ = eng.jk(d, want_k=False)
-    for v in (1, 17, 18):
+    for v in (1, 17, 18, 22, 23):
         eng.set_jk_variant(v)
         j2, k2 = eng.jk(d)
         assert np.abs(j2 - j).max() < 1e-10 and np.abs(k2 - k).max() < 1e-10
