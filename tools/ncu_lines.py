@@ -12,7 +12,8 @@ import tempfile
 
 rep, obj, pat = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 45
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+sel = ["-s", os.environ["NCU_LAUNCH"], "-c", "1"] if os.environ.get("NCU_LAUNCH") else []   # one launch of a multi-launch report
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]
 ia, isrc = hdr.index("Instructions Executed"), hdr.index("Source")

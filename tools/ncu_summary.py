@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep: key raw metrics + instruction mix + loop buckets (reads `ncu -i` CSV pages).
-usage: python tools/ncu_summary.py file.ncu-rep [out.txt]"""
+usage: python tools/ncu_summary.py file.ncu-rep [out.txt] [launch index in the report, default 0]"""
 import collections
 import csv
 import io
@@ -8,7 +8,8 @@ import sys
 
 rep = sys.argv[1]
 out = open(sys.argv[2], "w") if len(sys.argv) > 2 else sys.stdout
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+sel = ["-s", sys.argv[3], "-c", "1"] if len(sys.argv) > 3 else []     # pick one launch of a multi-launch report
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -23,7 +24,7 @@ keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
 for h, u, v in zip(hdr, units, vals):
     if h in keys or "issue_stalled" in h and "per_issue_active" in h:
         print(f"{h:90s} {v} {u}", file=out)
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]
 ia, isrc = hdr.index("Instructions Executed"), hdr.index("Source")
