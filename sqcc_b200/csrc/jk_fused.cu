@@ -28,6 +28,7 @@ struct JKParams {
     unsigned int *counter;
     double fx_scale;            // deterministic mode: 2^shift of the fixed-point accumulators
     unsigned long long *trace;  // optional (tuning): per warp {first task start, last task end, tasks done} in ns
+    int rotate;                 // each task starts its row-block list at a task-dependent offset (see jk_stream.cuh)
 };
 
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
@@ -364,6 +365,10 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
     p.ntasks = sc.n_tasks;
     p.counter = ctx->d_counter;
     p.trace = ctx->d_trace;
+    {
+        const char *e = getenv("SQCC_JK_ROTATE");   // tuning knob: 0 = every task walks its row-block list from the start
+        p.rotate = e ? atoi(e) : 1;
+    }
     p.fx_scale = 0.0;
     ctx->fx_scale = 0.0;
     if (ctx->jk_fixed) {

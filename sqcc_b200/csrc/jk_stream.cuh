@@ -49,6 +49,10 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, 
     else
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait()
@@ -131,6 +135,7 @@ __device__ __forceinline__ void flush_add(bool pred, double *ptr, double v, doub
 }
 
 constexpr int JK_RED_STRIDE = 17;  // value stride of the reduction scratch (odd: conflict-free 4x4 read pattern)
+constexpr int JK_RED_WIDE = 40;    // 32-entry rows: stride == 8 (mod 16) doubles, see JKSmem::WIDE_RED
 
 // NH: ring slots per sub-row.  NH = 2 (4 x 4 row-blocks): a slot holds HALF a piece (8 rows, 4 KB) and is handed back to
 // the producer as soon as its 8 rows are consumed, so the same 16 KB ring keeps up to 3 half-pieces (12 KB instead of 8 KB)
@@ -152,12 +157,18 @@ struct JKSmem {
     static constexpr int NRV = HALF ? 2 * NV : NV;           // values reduced per iteration (both half-warps)
     static constexpr int ROW_BYTES = HALF ? 256 : 512;       // one row of a ring slot / of the J~ slab
     static constexpr int STAGE_BYTES = (KS ? 2 : 1) * HR * ROW_BYTES;
-    static constexpr int RED_BUF = (NRV > 8 ? NRV : 8) * JK_RED_STRIDE;   // doubles per buffer (>= 8 values: J~ row dots go 8 at a time)
+    // WIDE_RED (4 x 2 dual-density pass, whole-warp chunks): the reduction scratch keeps all 32 lane partials of a value
+    // (no xor-16 fold before the store), rows of JK_RED_WIDE doubles read with conflict-free 128-bit loads, ONE buffer (the
+    // loads of an iteration are issued before the warp barrier its stores follow).
+    static constexpr bool WIDE_RED = NB == 2 && HM == 0;
+    static constexpr int RED_STRIDE = WIDE_RED ? JK_RED_WIDE : JK_RED_STRIDE;
+    static constexpr int RED_NBUF = WIDE_RED ? 1 : 2;
+    static constexpr int RED_BUF = (NRV > 8 ? NRV : 8) * RED_STRIDE;   // doubles per buffer (>= 8 values: J~ row dots go 8 at a time)
     static constexpr int OFF_SLAB = 0;                                   // double2 [16][32 | 16]
     static constexpr int OFF_RING = OFF_SLAB + (SLAB ? JK_KN * ROW_BYTES : 0); // [STAGES][HR][ROW_BYTES]
     static constexpr int OFF_U = OFF_RING + STAGES * STAGE_BYTES;        // double [NSP][16][NVE]
-    static constexpr int OFF_RED = OFF_U + NSP * JK_KN * NVE * 8;        // double [2][RED_BUF]
-    static constexpr int OFF_KOUT = OFF_RED + 2 * RED_BUF * 8;           // double [NRV][17]
+    static constexpr int OFF_RED = OFF_U + NSP * JK_KN * NVE * 8;        // double [RED_NBUF][RED_BUF]
+    static constexpr int OFF_KOUT = OFF_RED + RED_NBUF * RED_BUF * 8;    // double [NRV][17]
     static constexpr int OFF_W = OFF_KOUT + ((NRV + 1) & ~1) * JK_RED_STRIDE * 8;     // double [R]
     static constexpr int OFF_BAR = OFF_W + R * 8;                        // u64 [STAGES]
     static constexpr int WARP_BYTES = (OFF_BAR + STAGES * 8 + 63) & ~63;
@@ -185,6 +196,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
     constexpr int KSTEP = KS ? 2 : 1;                 // sub-rows per loop iteration
     constexpr int NVP = (NV + 7) / 8;
     constexpr bool DEEP = NB == 4;   // reduction pipeline over three iterations (needs NV more live registers) or two
+    constexpr bool WIDE = SM::WIDE_RED;   // 32 lane partials per value in the scratch, no xor-16 fold (JKSmem)
+    constexpr int RW = WIDE ? 8 : 4;      // scratch entries one lane sums per value
+    static_assert(!WIDE || (!DEEP && !HALF), "wide reduction rows: shallow pipeline, whole-warp chunks");
     constexpr uint32_t STAGE_BYTES = SM::STAGE_BYTES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -238,11 +252,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             for (int kk = 0; kk < JK_KN; ++kk) s_jt[kk * LW + ql] = make_double2(0.0, 0.0);
         }
 
-        // row-block list of the task, one entry per lane (rb_count <= 32)
+        // row-block list of the task, one entry per lane (rb_count <= 32).  The tasks that share a group of row-blocks
+        // (other k-ranges / chunks) are neighbours in the queue and run at the same time on other warps; walking the list
+        // in the same order they would all flush K~[j, l] / K~[j, k] of the SAME rows j at the same moment, and atomics on
+        // one address serialise in L2.  Every task therefore starts at its own offset into the (cyclic) list.
         long long my_base = 0;
         int my_imax = k0, my_j0 = 0;
         if (lane < task.rb_count) {
-            const RowBlock rbk = p.rowblocks[task.rb_begin + lane];
+            int src = lane + (p.rotate ? (int)((t * 40503u >> 3) % (unsigned)task.rb_count) : 0);
+            if (src >= task.rb_count) src -= task.rb_count;
+            const RowBlock rbk = p.rowblocks[task.rb_begin + src];
             my_base = rbk.base;
             my_imax = rbk.imax;
             my_j0 = rbk.j0;
@@ -288,7 +307,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 // sub-row 2 it + hh (zero-filled past the piece width and past the last sub-row of the sweep)
                 const uint32_t nb = (xcol < w && hh < prod_left) ? 16u : 0u;
                 const char *src = half_src + 16 * ql + (size_t)(hh < prod_left ? hh : 0) * (LAY_ROWS * 8) * w;
-                const uint32_t d = dst + 16 * ql + hh * (LAY_ROWS * 256);
+                const uint32_t d = dst + 16 * ql + hh * (R * 256);
                 if (w == 32) {
 #pragma unroll
                     for (int r = 0; r < R; ++r) cp_async16_zfill<HINT>(d + r * 256, src + r * 32 * 8, nb, pol_stream);
@@ -367,19 +386,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         };
 
         // reduction helpers (pass h handles values 8h .. 8h+7: value 8h + (lane >> 2), 4 lanes per value, 4 entries each)
-        const int red_rd_off = (lane >> 2) * JK_RED_STRIDE + (lane & 3) * 4;
+        const int accj_rd_off = (lane >> 2) * JK_RED_STRIDE + (lane & 3) * 4;
+        // (WIDE: quad lane q reads entries 2q, 2q+1 (+ 8 e) of its value: 128-bit loads, conflict-free with the row stride 40)
+        const int red_rd_off = WIDE ? (lane >> 2) * JK_RED_WIDE + (lane & 3) * 2 : accj_rd_off;
 
-        // Operands of a row-block that come from global memory (an L2 round trip takes 1-2 us under the stream's load): they
-        // are fetched into registers BEFORE the previous row-block's epilogue (drain, flushes) and committed after it.
-        //   nx_dj        D_s[j_b, l0..l0+1]                         (lane operands)
-        //   nx_w         D2[i_a, j_b], r = 4 b + a                  (lane r < R; row indices clamped into range: operands of
-        //   nx_u[q]      D_s[row_q, k0 + lane], q = s*(4+NB) + (a | 4+b)   lanes < 16   rows outside the canonical range
-        //                                                                                only ever meet stored zeros)
+        // Operands of a row-block that come from global memory (an L2 round trip takes 1-2 us under the stream's load) are
+        // fetched BEFORE the previous row-block's epilogue (drain, flushes):
+        //   nx_dj          D_s[j_b, l0..l0+1]                       lane operands, into registers
+        //   s_w[r]         D2[i_a, j_b], r = 4 b + a                8-byte cp.async straight into shared memory (registers
+        //   s_u[kk][q]     D_s[row_q, k0 + kk], q = s*(4+NB) + (a | 4+b)   held across the epilogue were spilled, and the spill
+        //                                                           store waits for the load it was meant to overlap)
+        // Row indices are clamped into range: operands of rows outside the canonical range only ever meet stored zeros.
+        // (whole-warp chunks: the NV values of sub-row k0 + (lane & 15) are split over the two half-warps, NUH each)
+        constexpr int NUH = HALF ? NV : NV / 2;
+        static_assert(HALF || NV % 2 == 0, "operand prefetch splits the values over the half-warps");
         double2 nx_dj[NS][NB];
-        double nx_w = 0.0, nx_u[NV];
         auto fetch_rb = [&](int rbi) {
             const int imax = __shfl_sync(0xffffffffu, my_imax, rbi), j0 = __shfl_sync(0xffffffffu, my_j0, rbi);
             const int i0 = imax - 3;
+            __syncwarp();   // every lane is done with s_w / s_u of the previous sweep
 #pragma unroll
             for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -391,20 +416,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 int i = i0 + (lane & 3), j = j0 + ((lane >> 2) & (NB - 1));
                 i = i < 0 ? 0 : i;
                 j = j < n ? j : n - 1;
-                nx_w = __ldg(p.d2 + (size_t)i * ldd + j);
+                if (lane < R) cp_async8(smem_u32(s_w + lane), p.d2 + (size_t)i * ldd + j);
             }
             if (WANTK) {
                 // 32-bit indexing: nspin * n * ldd < 2^31 for every supported n
                 const int k = (k0 + (lane & 15)) < n ? (k0 + (lane & 15)) : n - 1;
                 const double *dk = dsp_l + k;
+                const uint32_t su = smem_u32(s_u + (sp * JK_KN + (lane & 15)) * NVE + (HALF ? 0 : (lane >> 4) * NUH));
+                if (!KS || lane < JK_KN) {   // (KS: one density, rows kk = 0..15 staged by the first half-warp)
 #pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const int s = q / (NI + NB), wq = q % (NI + NB);
-                    int row = wq < NI ? i0 + wq : j0 + (wq - NI);
-                    row = row < 0 ? 0 : (row < n ? row : n - 1);
-                    nx_u[q] = __ldg(dk + (s * n + row) * ldd);
+                    for (int qq = 0; qq < NUH; ++qq) {
+                        const int q = HALF ? qq : (lane >> 4) * NUH + qq;
+                        const int s = q / (NI + NB), wq = q % (NI + NB);
+                        int row = wq < NI ? i0 + wq : j0 + (wq - NI);
+                        row = row < 0 ? 0 : (row < n ? row : n - 1);
+                        cp_async8(su + 8 * qq, dk + (s * n + row) * ldd);
+                    }
                 }
             }
+            cp_async_commit();
         };
         fetch_rb(0);
 
@@ -436,33 +466,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             double accJ[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) accJ[r] = 0.0;
-            // commit the prefetched warp-uniform operands to shared memory:
-            //   s_w[r]      = D2[i_a, j_b], r = 4 b + a
-            //   s_u[kk][q]  = D_s[row_q, k0+kk], q = s*(NI+NB) + (a | NI+b)
-            __syncwarp();
-            if (lane < R) s_w[lane] = nx_w;
-            if (WANTK && (SPIN2 || lane < JK_KN)) {   // (KS: one density, rows kk = 0..15 staged by the first half-warp)
-                double *su = s_u + (sp * JK_KN + (lane & 15)) * NVE;
-#pragma unroll
-                for (int q = 0; q < NV; ++q) su[q] = nx_u[q];
-            }
-            // destinations of the reduced K~[row_q, k0 + kk] values: lane = kk + 16 (q & 1), pass m covers q = 2m, 2m+1
-            // (SPIN2: 16 values, value V = 8 spin + q, pass m covers V = 2m, 2m+1.  KS: 16 values V = 8 parity + q in 8
-            //  iteration columns: lane = it + 8 (V & 3), pass m covers V = 4m .. 4m+3, sub-row kk = 2 it + (V >> 3))
+            // the prefetched warp-uniform operands s_w / s_u have landed (the group committed by fetch_rb is the newest one:
+            // with it every older group -- ring slots of the cp.async path -- is complete as well); the warp barrier at the
+            // top of the first iteration makes them visible to all lanes
+            cp_async_wait<0>();
             constexpr int NKV = HALF ? 16 : NV;
             constexpr int NKP = KS ? 4 : (NKV + 1) / 2;
-            double *kout_dst[NKP];
-            bool kout_ok[NKP];
-#pragma unroll
-            for (int m = 0; m < NKP; ++m) {
-                const int qv = KS ? 4 * m + (lane >> 3) : 2 * m + (lane >> 4);
-                const int q = HALF ? (qv & 7) : qv;
-                const int s = SPIN2 ? (qv >> 3) : (KS ? 0 : q / (NI + NB)), wq = q % (NI + NB);
-                const int row = wq < NI ? i0 + wq : j0 + (wq - NI);
-                const int kkq = KS ? 2 * (lane & 7) + (qv >> 3) : (lane & 15);
-                kout_ok[m] = WANTK && qv < NKV && row >= 0 && row < n && kkq < nkk;
-                kout_dst[m] = p.kt + (kout_ok[m] ? s * nl + (size_t)row * ldd + k0 + kkq : 0);
-            }
 
             double cdp[NV];   // lane partials of the previous sub-row, published one iteration later
 #pragma unroll
@@ -482,7 +491,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
 
             // one ring slot: wait for the previous half-iteration in every lane (its slot is free, its shared-memory stores are
             // visible), refill the freed slot, wait for the oldest one
-            auto next_slot = [&]() -> const double2 * {
+            auto slot_wait = [&]() {
                 __syncwarp();
                 if (prod_todo > 0) issue_next();
                 if (full) {
@@ -492,26 +501,42 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     cp_async_commit();
                     cp_async_wait<STAGES - 1>();   // this lane's 16 bytes of every row of the oldest slot have landed
                 }
+            };
+            auto slot_ready = [&]() -> const double2 * {
                 __syncwarp();   // converged from here to the end of the block: no divergent branch below (ptxas can then
                                 // schedule the shuffles into the DFMA block instead of fencing them with BRA.DIV)
-                const double2 *buf = ring + (size_t)stage_r * (STAGE_BYTES / 16) + (KS ? hh * (LAY_ROWS * LW) : 0) + ql;
+                const double2 *buf = ring + (size_t)stage_r * (STAGE_BYTES / 16) + (KS ? hh * (R * LW) : 0) + ql;
                 stage_r = (stage_r + 1 == STAGES) ? 0 : stage_r + 1;
                 return buf;
             };
 
 #pragma unroll 2
             for (int kk = 0; kk < nit; ++kk) {   // (KS: kk counts iterations of two sub-rows, this lane's is kl)
-                const double2 *buf = next_slot();
+                slot_wait();
                 const int kl = KS ? ((2 * kk + hh) < JK_KN ? 2 * kk + hh : JK_KN - 1) : kk;
 
                 // ---- C, loads: partials of sub-row kk-2 (buffer kk & 1; kk-1 and buffer (kk-1) & 1 in the shallow pipeline)
                 // (SPIN2: 16 values x 16 entries: value lane >> 1, two lanes per value, 8 entries each)
-                double r4[NVP][4], r8[8];
+                // (WIDE: one buffer; its loads stand before the warp barrier of slot_ready(), this iteration's stores after it)
+                double r4[NVP][RW], r8[8];
+                if (WANTK && WIDE) {
+                    const double *rd = s_red + red_rd_off;
+#pragma unroll
+                    for (int h = 0; h < NVP; ++h)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const double2 t2 = *reinterpret_cast<const double2 *>(
+                                rd + (8 * h < NV - 8 ? 8 * h : (NV > 8 ? NV - 8 : 0)) * JK_RED_WIDE + 8 * e);
+                            r4[h][2 * e] = t2.x;
+                            r4[h][2 * e + 1] = t2.y;
+                        }
+                }
+                const double2 *buf = slot_ready();
                 if (WANTK && HALF) {
                     const double *rd = s_red + (kk & 1) * SM::RED_BUF + (lane >> 1) * JK_RED_STRIDE + (lane & 1) * 8;
 #pragma unroll
                     for (int e = 0; e < 8; ++e) r8[e] = rd[e];
-                } else if (WANTK) {
+                } else if (WANTK && !WIDE) {
                     const double *rd = s_red + ((DEEP ? kk : kk + 1) & 1) * SM::RED_BUF + red_rd_off;
 #pragma unroll
                     for (int h = 0; h < NVP; ++h)
@@ -525,7 +550,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     d2n = d2nn;
                     d2nn = load_d2(d2p, lane_in && KSTEP * (kk + 2) + hoff < nkk);
                 } else {
-                    d2n = load_d2(d2p, lane_in && kk + 1 < nkk);
+                    // unconditional (a predicated load costs a select and a register move that waits for the data at the
+                    // end of the iteration): past the sweep / the matrix it reads rows of the next plane of the work
+                    // buffer, which meet stored zeros or are never used
+                    d2n = HINT ? ldg2_keep(d2p, pol_keep) : ldg2(d2p);
                 }
                 double u[NVE];
                 if (WANTK) {
@@ -580,6 +608,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
 #pragma unroll
                     for (int h = 0; h < NVP; ++h) {
                         double sum = (r4[h][0] + r4[h][1]) + (r4[h][2] + r4[h][3]);
+                        if (WIDE) sum += (r4[h][RW - 4] + r4[h][RW - 3]) + (r4[h][RW - 2] + r4[h][RW - 1]);
                         sum += shfl_xor_f64(sum, 1);
                         sum += shfl_xor_f64(sum, 2);
                         csum[h] = sum;
@@ -594,7 +623,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     }
                 }
                 if (NH == 2) {
-                    const double2 *buf1 = next_slot();
+                    slot_wait();
+                    const double2 *buf1 = slot_ready();
                     fma_rows(buf1, 1);
                 }
                 double2 cur = SLAB ? s_jt[kl * LW + ql] : make_double2(0.0, 0.0);
@@ -604,7 +634,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
 #pragma unroll
                         for (int q = 0; q < NV; ++q) cdp[q] = cd[q];
                     }
-                    if (!HALF) {   // (half-warp modes: the 16 lanes of a half-warp publish their own partials, nothing to fold)
+                    if (!HALF && !WIDE) {   // (half-warp modes: the 16 lanes of a half-warp publish their own partials, nothing
+                                            //  to fold; WIDE: all 32 lanes publish)
 #pragma unroll
                         for (int q = 0; q < NV; ++q) cdp[q] += shfl_xor_f64(cdp[q], 16);
                     }
@@ -623,9 +654,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     flush_add<FIXED>(true, dst + 1, cur.y, fx);
                 }
                 if (WANTK) {
-                    double *wr = s_red + ((DEEP ? kk + 1 : kk) & 1) * SM::RED_BUF + hh * (NV * JK_RED_STRIDE) + (lane & 15);
+                    double *wr = WIDE ? s_red + lane
+                                      : s_red + ((DEEP ? kk + 1 : kk) & 1) * SM::RED_BUF + hh * (NV * JK_RED_STRIDE) + (lane & 15);
 #pragma unroll
-                    for (int q = 0; q < NV; ++q) wr[q * JK_RED_STRIDE] = cdp[q];
+                    for (int q = 0; q < NV; ++q) wr[q * SM::RED_STRIDE] = cdp[q];
                     if (DEEP) {
 #pragma unroll
                         for (int q = 0; q < NV; ++q) cdp[q] = cd[q];
@@ -662,25 +694,41 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                         if ((lane & 1) == 0 && ks >= 0) s_kout[(lane >> 1) * JK_RED_STRIDE + ks] = sum;
                         continue;
                     }
-                    const double *rd = s_red + ((nit + d) & 1) * SM::RED_BUF + red_rd_off;
+                    const double *rd = s_red + (WIDE ? 0 : ((nit + d) & 1) * SM::RED_BUF) + red_rd_off;
 #pragma unroll
                     for (int h = 0; h < NVP; ++h) {
                         const int v = 8 * h + (lane >> 2);
                         double sum = 0.0;
-                        if (v < NV) sum = (rd[8 * h * JK_RED_STRIDE] + rd[8 * h * JK_RED_STRIDE + 1]) +
-                                          (rd[8 * h * JK_RED_STRIDE + 2] + rd[8 * h * JK_RED_STRIDE + 3]);
+                        if (WIDE) {
+                            if (v < NV) {
+                                const double *rv = rd + 8 * h * JK_RED_WIDE;
+                                sum = ((rv[0] + rv[1]) + (rv[8] + rv[9])) + ((rv[16] + rv[17]) + (rv[24] + rv[25]));
+                            }
+                        } else if (v < NV)
+                            sum = (rd[8 * h * JK_RED_STRIDE] + rd[8 * h * JK_RED_STRIDE + 1]) +
+                                  (rd[8 * h * JK_RED_STRIDE + 2] + rd[8 * h * JK_RED_STRIDE + 3]);
                         sum += shfl_xor_f64(sum, 1);
                         sum += shfl_xor_f64(sum, 2);
                         if ((lane & 3) == 0 && v < NV && ks >= 0) s_kout[v * JK_RED_STRIDE + ks] = sum;
                     }
                 }
                 __syncwarp();
-                // reduced K~[row_q, k0 .. k0+nkk) leave with coalesced reds (16 consecutive k per value)
+                // reduced K~[row_q, k0 .. k0+nkk) leave with coalesced reds (16 consecutive k per value): lane = kk + 16 (q & 1),
+                // pass m covers q = 2m, 2m+1
+                // (SPIN2: 16 values, value V = 8 spin + q, pass m covers V = 2m, 2m+1.  KS: 16 values V = 8 parity + q in 8
+                //  iteration columns: lane = it + 8 (V & 3), pass m covers V = 4m .. 4m+3, sub-row kk = 2 it + (V >> 3))
+                // (the destinations are computed here, not before the sweep: live across the loop they were spilled, and a
+                //  local-memory reload is an L2 round trip with the whole L1 carved out as shared memory)
 #pragma unroll
                 for (int m = 0; m < NKP; ++m) {
-                    const int q = KS ? 4 * m + (lane >> 3) : 2 * m + (lane >> 4);
-                    const double v = q < NKV ? s_kout[q * JK_RED_STRIDE + (KS ? (lane & 7) : (lane & 15))] : 0.0;
-                    flush_add<FIXED>(kout_ok[m], kout_dst[m], v, fx);
+                    const int qv = KS ? 4 * m + (lane >> 3) : 2 * m + (lane >> 4);
+                    const int q = HALF ? (qv & 7) : qv;
+                    const int s = SPIN2 ? (qv >> 3) : (KS ? 0 : q / (NI + NB)), wq = q % (NI + NB);
+                    const int row = wq < NI ? i0 + wq : j0 + (wq - NI);
+                    const int kkq = KS ? 2 * (lane & 7) + (qv >> 3) : (lane & 15);
+                    const bool ok = qv < NKV && row >= 0 && row < n && kkq < nkk;
+                    const double v = qv < NKV ? s_kout[qv * JK_RED_STRIDE + (KS ? (lane & 7) : (lane & 15))] : 0.0;
+                    flush_add<FIXED>(ok, p.kt + (ok ? s * nl + (size_t)row * ldd + k0 + kkq : 0), v, fx);
                 }
 #pragma unroll
                 for (int s = 0; s < NS; ++s)
@@ -708,7 +756,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     }
                     __syncwarp();
                     const int v = 8 * h + (lane >> 2);
-                    const double *rd = s_red + red_rd_off;
+                    const double *rd = s_red + accj_rd_off;
                     double sum = 0.0;
                     if (v < R) sum = (rd[0] + rd[1]) + (rd[2] + rd[3]);
                     sum += shfl_xor_f64(sum, 1);
@@ -721,7 +769,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         }
         flushA();
         __syncwarp();
-        const int imax0 = __shfl_sync(0xffffffffu, my_imax, 0);   // the list is i-descending: longest sweep first
+        int imax0 = my_imax;   // longest sweep of the task (lanes without a row-block hold k0)
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const int other = __shfl_xor_sync(0xffffffffu, imax0, o);
+            imax0 = other > imax0 ? other : imax0;
+        }
         if (SLAB && lane_in && sp == 0) {
             const int kmax = imax0 + 1 - k0 < JK_KN ? imax0 + 1 - k0 : JK_KN;
             for (int kk = KS ? hh : 0; kk < kmax; kk += KSTEP) {   // (KS: the half-warp that owns the row's parity)
