@@ -96,7 +96,7 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uin
 __device__ __forceinline__ double2 ldg2_keep(const double *p, uint64_t pol)
 {
     double2 r;
-    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
     return r;
 }
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
@@ -171,7 +171,14 @@ struct JKSmem {
     static constexpr int OFF_KOUT = OFF_RED + RED_NBUF * RED_BUF * 8;    // double [NRV][17]
     static constexpr int OFF_W = OFF_KOUT + ((NRV + 1) & ~1) * JK_RED_STRIDE * 8;     // double [R]
     static constexpr int OFF_BAR = OFF_W + R * 8;                        // u64 [STAGES]
-    static constexpr int WARP_BYTES = (OFF_BAR + STAGES * 8 + 63) & ~63;
+    // D2F: the density tile row D2[k0, chunk] every sweep of a task starts with is kept in shared memory (one double2 per
+    // lane) instead of being re-fetched through L2 at the top of every sweep, where nothing hides the round trip
+    static constexpr bool D2F = NB == 2 && HM == 0;
+    static constexpr int OFF_D2F = (OFF_BAR + STAGES * 8 + 15) & ~15;    // double2 [32]
+    // (same pass: the row-block list of the task lives in shared memory instead of one entry per lane + shuffles -- the
+    //  pass has no registers to spare, and a spilled register is an L2 round trip)
+    static constexpr int OFF_RB = OFF_D2F + (D2F ? 512 : 0);            // RowBlock [32]
+    static constexpr int WARP_BYTES = (OFF_RB + (D2F ? 512 : 0) + 63) & ~63;
 };
 
 // NB: rows j per row-block (4: RHF / J-only, 2: UHF).  TMA: full pieces through cp.async.bulk (false: cp.async only).
@@ -212,6 +219,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
     double *s_red = reinterpret_cast<double *>(wbase + SM::OFF_RED);
     double *s_kout = reinterpret_cast<double *>(wbase + SM::OFF_KOUT);
     double *s_w = reinterpret_cast<double *>(wbase + SM::OFF_W);
+    double2 *s_d2f = reinterpret_cast<double2 *>(wbase + SM::OFF_D2F);
+    RowBlock *s_rb = reinterpret_cast<RowBlock *>(wbase + SM::OFF_RB);
+    constexpr bool RBS = SM::D2F;
     const uint32_t ring_u32 = smem_u32(wbase + SM::OFF_RING);
     const uint32_t bar_u32 = smem_u32(wbase + SM::OFF_BAR);
     const int n = p.n, ldd = p.ldd;
@@ -266,6 +276,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             my_imax = rbk.imax;
             my_j0 = rbk.j0;
         }
+        if (RBS) {
+            s_rb[lane] = RowBlock{my_base, my_imax, my_j0};
+            __syncwarp();
+        }
+        auto rb_imax = [&](int idx) { return RBS ? s_rb[idx].imax : __shfl_sync(0xffffffffu, my_imax, idx); };
+        auto rb_j0 = [&](int idx) { return RBS ? s_rb[idx].j0 : __shfl_sync(0xffffffffu, my_j0, idx); };
+        auto rb_base = [&](int idx) { return RBS ? (long long)s_rb[idx].base : __shfl_sync(0xffffffffu, my_base, idx); };
         // sub-rows to stream in this task
         int total_it = 0;
         {
@@ -283,9 +300,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         auto issue_next = [&]() {
             if (prod_left == 0) {   // next row-block of the list
                 ++prod_rbi;
-                const long long base = __shfl_sync(0xffffffffu, my_base, prod_rbi);
-                const int imax = __shfl_sync(0xffffffffu, my_imax, prod_rbi);
-                const int j0 = __shfl_sync(0xffffffffu, my_j0, prod_rbi);
+                const long long base = rb_base(prod_rbi);
+                const int imax = rb_imax(prod_rbi);
+                const int j0 = rb_j0(prod_rbi);
                 prod_left = imax + 1 - k0 < JK_KN ? imax + 1 - k0 : JK_KN;
                 long long off = base + lay_piece_offset(imax, c, k0);
                 if (NB == 2) off += (long long)((j0 >> 1) & 1) * 8 * w;   // second 4 x 2 half of the tile's pieces
@@ -402,7 +419,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         static_assert(HALF || NV % 2 == 0, "operand prefetch splits the values over the half-warps");
         double2 nx_dj[NS][NB];
         auto fetch_rb = [&](int rbi) {
-            const int imax = __shfl_sync(0xffffffffu, my_imax, rbi), j0 = __shfl_sync(0xffffffffu, my_j0, rbi);
+            const int imax = rb_imax(rbi), j0 = rb_j0(rbi);
             const int i0 = imax - 3;
             __syncwarp();   // every lane is done with s_w / s_u of the previous sweep
 #pragma unroll
@@ -436,10 +453,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             }
             cp_async_commit();
         };
+        if (SM::D2F)   // joins the group fetch_rb commits; every lane reads back only the 16 bytes it copies itself
+            cp_async16_zfill<HINT>(smem_u32(s_d2f + lane), p.d2 + (size_t)k0 * ldd + (lane_in ? l0 : 0), 16u, pol_keep);
         fetch_rb(0);
 
         for (int rbi = 0; rbi < task.rb_count; ++rbi) {
-            const int imax = __shfl_sync(0xffffffffu, my_imax, rbi), j0 = __shfl_sync(0xffffffffu, my_j0, rbi);
+            const int imax = rb_imax(rbi), j0 = rb_j0(rbi);
             const int i0 = imax - 3;   // may be negative in the clipped lowest i-block: those rows hold zeros
             const int nkk = imax + 1 - k0 < JK_KN ? imax + 1 - k0 : JK_KN;
             if (i0 != cur_i0) {
@@ -485,7 +504,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 return on ? (HINT ? ldg2_keep(q, pol_keep) : ldg2(q)) : make_double2(0.0, 0.0);
             };
             constexpr bool D2_TWO = NB == 4;   // the dual-density pass has no registers to spare: one sub-row ahead
-            double2 d2n = load_d2(d2p, lane_in && hoff < nkk);
+            double2 d2n = SM::D2F ? s_d2f[lane] : load_d2(d2p, lane_in && hoff < nkk);
             double2 d2nn = D2_TWO ? load_d2(d2p + KSTEP * ldd, lane_in && KSTEP + hoff < nkk) : make_double2(0.0, 0.0);
             if (D2_TWO) d2p += KSTEP * ldd;
 
@@ -665,6 +684,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 }
             }
             if (rbi + 1 < task.rb_count) fetch_rb(rbi + 1);   // in flight during the epilogue below
+            {   // ---- epilogue of the row-block
+            // (RBS: the row-block's scalars are re-read from shared memory here -- kept live across the sweep they were spilled)
+            const int imax_pre = imax, j0_pre = j0;
+            const int imax = RBS ? reinterpret_cast<const volatile RowBlock *>(s_rb)[rbi].imax : imax_pre;
+            const int j0 = RBS ? reinterpret_cast<const volatile RowBlock *>(s_rb)[rbi].j0 : j0_pre;
+            const int i0 = imax - 3;
+            const int nkk = imax + 1 - k0 < JK_KN ? imax + 1 - k0 : JK_KN;
+            const int nit = KS ? (nkk + 1) >> 1 : nkk;
             // ---- drain the reduction pipeline: sub-rows nkk-2 (published, not summed) and nkk-1 (not yet published)
             if (WANTK) {
                 __syncwarp();
@@ -766,10 +793,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     flush_add<FIXED>(ok, p.jt + (ok ? (size_t)i * ldd + j : 0), sum, fx);
                 }
             }
+            }
         }
         flushA();
         __syncwarp();
-        int imax0 = my_imax;   // longest sweep of the task (lanes without a row-block hold k0)
+        int imax0 = RBS ? s_rb[lane].imax : my_imax;   // longest sweep of the task (lanes without a row-block hold k0)
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
             const int other = __shfl_xor_sync(0xffffffffu, imax0, o);
