@@ -171,14 +171,11 @@ struct JKSmem {
     static constexpr int OFF_KOUT = OFF_RED + RED_NBUF * RED_BUF * 8;    // double [NRV][17]
     static constexpr int OFF_W = OFF_KOUT + ((NRV + 1) & ~1) * JK_RED_STRIDE * 8;     // double [R]
     static constexpr int OFF_BAR = OFF_W + R * 8;                        // u64 [STAGES]
-    // D2F: the density tile row D2[k0, chunk] every sweep of a task starts with is kept in shared memory (one double2 per
-    // lane) instead of being re-fetched through L2 at the top of every sweep, where nothing hides the round trip
-    static constexpr bool D2F = NB == 2 && HM == 0;
-    static constexpr int OFF_D2F = (OFF_BAR + STAGES * 8 + 15) & ~15;    // double2 [32]
-    // (same pass: the row-block list of the task lives in shared memory instead of one entry per lane + shuffles -- the
-    //  pass has no registers to spare, and a spilled register is an L2 round trip)
-    static constexpr int OFF_RB = OFF_D2F + (D2F ? 512 : 0);            // RowBlock [32]
-    static constexpr int WARP_BYTES = (OFF_RB + (D2F ? 512 : 0) + 63) & ~63;
+    // RBS (dual-density pass): the row-block list of the task lives in shared memory instead of one entry per lane +
+    // shuffles -- the pass has no registers to spare, and a spilled register is an L2 round trip
+    static constexpr bool RBS = NB == 2 && HM == 0;
+    static constexpr int OFF_RB = (OFF_BAR + STAGES * 8 + 15) & ~15;     // RowBlock [32]
+    static constexpr int WARP_BYTES = (OFF_RB + (RBS ? 512 : 0) + 63) & ~63;
 };
 
 // NB: rows j per row-block (4: RHF / J-only, 2: UHF).  TMA: full pieces through cp.async.bulk (false: cp.async only).
@@ -219,9 +216,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
     double *s_red = reinterpret_cast<double *>(wbase + SM::OFF_RED);
     double *s_kout = reinterpret_cast<double *>(wbase + SM::OFF_KOUT);
     double *s_w = reinterpret_cast<double *>(wbase + SM::OFF_W);
-    double2 *s_d2f = reinterpret_cast<double2 *>(wbase + SM::OFF_D2F);
     RowBlock *s_rb = reinterpret_cast<RowBlock *>(wbase + SM::OFF_RB);
-    constexpr bool RBS = SM::D2F;
+    constexpr bool RBS = SM::RBS;
     const uint32_t ring_u32 = smem_u32(wbase + SM::OFF_RING);
     const uint32_t bar_u32 = smem_u32(wbase + SM::OFF_BAR);
     const int n = p.n, ldd = p.ldd;
@@ -453,8 +449,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             }
             cp_async_commit();
         };
-        if (SM::D2F)   // joins the group fetch_rb commits; every lane reads back only the 16 bytes it copies itself
-            cp_async16_zfill<HINT>(smem_u32(s_d2f + lane), p.d2 + (size_t)k0 * ldd + (lane_in ? l0 : 0), 16u, pol_keep);
+        // Density tile rows D2[k0 + kk, l-chunk] (the same 16 rows for every sweep of the task): loaded AHEAD of their sub-row
+        // (an L2 hit queues behind the ERI stream and takes longer than one iteration under load) -- two sub-rows for the
+        // single-density shapes, one for the dual-density pass (no registers to spare) -- and the last iterations of a
+        // sweep fetch the first rows of the NEXT sweep, so no sweep starts by waiting for an L2 round trip.  The loads
+        // are unconditional (a predicated load costs a select and a register move that waits for the data at the end of
+        // the iteration): rows past the matrix come from the next plane of the work buffer and only meet stored zeros.
+        constexpr bool D2_TWO = NB == 4;
+        constexpr int D2_AHEAD = D2_TWO ? 2 : 1;
+        const double *d2base = p.d2 + (size_t)(k0 + (KS ? hh : 0)) * ldd + (lane_in ? l0 : 0);
+        auto load_d2 = [&](int row) { return HINT ? ldg2_keep(d2base + (size_t)row * ldd, pol_keep) : ldg2(d2base + (size_t)row * ldd); };
+        double2 d2n = load_d2(0);
+        double2 d2nn = D2_TWO ? load_d2(KSTEP) : make_double2(0.0, 0.0);
         fetch_rb(0);
 
         for (int rbi = 0; rbi < task.rb_count; ++rbi) {
@@ -495,18 +501,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             double cdp[NV];   // lane partials of the previous sub-row, published one iteration later
 #pragma unroll
             for (int q = 0; q < NV; ++q) cdp[q] = 0.0;
-            // density tile row D2[k0 + kk, l-chunk]: loaded TWO sub-rows ahead (an L2 hit queues behind the ERI stream and
-            // takes longer than one iteration under load)
-            const int hoff = KS ? hh : 0;                      // sub-row of this lane inside an iteration
             const int nit = KS ? (nkk + 1) >> 1 : nkk;         // loop iterations of this sweep
-            const double *d2p = p.d2 + (size_t)(k0 + hoff) * ldd + (lane_in ? l0 : 0);
-            auto load_d2 = [&](const double *q, bool on) {
-                return on ? (HINT ? ldg2_keep(q, pol_keep) : ldg2(q)) : make_double2(0.0, 0.0);
-            };
-            constexpr bool D2_TWO = NB == 4;   // the dual-density pass has no registers to spare: one sub-row ahead
-            double2 d2n = SM::D2F ? s_d2f[lane] : load_d2(d2p, lane_in && hoff < nkk);
-            double2 d2nn = D2_TWO ? load_d2(d2p + KSTEP * ldd, lane_in && KSTEP + hoff < nkk) : make_double2(0.0, 0.0);
-            if (D2_TWO) d2p += KSTEP * ldd;
 
             // one ring slot: wait for the previous half-iteration in every lane (its slot is free, its shared-memory stores are
             // visible), refill the freed slot, wait for the oldest one
@@ -564,15 +559,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 }
                 // ---- A: the FMA block of sub-row kk
                 const double2 d2 = d2n;
-                d2p += KSTEP * ldd;
-                if (D2_TWO) {
-                    d2n = d2nn;
-                    d2nn = load_d2(d2p, lane_in && KSTEP * (kk + 2) + hoff < nkk);
-                } else {
-                    // unconditional (a predicated load costs a select and a register move that waits for the data at the
-                    // end of the iteration): past the sweep / the matrix it reads rows of the next plane of the work
-                    // buffer, which meet stored zeros or are never used
-                    d2n = HINT ? ldg2_keep(d2p, pol_keep) : ldg2(d2p);
+                {
+                    const int ahead = kk + D2_AHEAD;   // iteration whose row is fetched now (wraps into the next sweep)
+                    const double2 nx = load_d2(KSTEP * (ahead < nit ? ahead : ahead - nit));
+                    d2n = D2_TWO ? d2nn : nx;
+                    if (D2_TWO) d2nn = nx;
                 }
                 double u[NVE];
                 if (WANTK) {
@@ -683,6 +674,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     }
                 }
             }
+            if (D2_TWO && nit == 1) d2n = load_d2(0);   // (one-iteration sweep: its look-ahead of two skipped the next row 0)
             if (rbi + 1 < task.rb_count) fetch_rb(rbi + 1);   // in flight during the epilogue below
             {   // ---- epilogue of the row-block
             // (RBS: the row-block's scalars are re-read from shared memory here -- kept live across the sweep they were spilled)
