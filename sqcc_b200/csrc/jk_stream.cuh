@@ -163,7 +163,8 @@ struct JKSmem {
     static constexpr bool WIDE_RED = NB == 2 && HM == 0;
     static constexpr int RED_STRIDE = WIDE_RED ? JK_RED_WIDE : JK_RED_STRIDE;
     static constexpr int RED_NBUF = WIDE_RED ? 1 : 2;
-    static constexpr int RED_BUF = (NRV > 8 ? NRV : 8) * RED_STRIDE;   // doubles per buffer (>= 8 values: J~ row dots go 8 at a time)
+    // doubles per buffer (>= 8 values: J~ row dots go 8 at a time; the last wide row needs no padding)
+    static constexpr int RED_BUF = WIDE_RED ? (NRV - 1) * JK_RED_WIDE + 32 : (NRV > 8 ? NRV : 8) * RED_STRIDE;
     static constexpr int OFF_SLAB = 0;                                   // double2 [16][32 | 16]
     static constexpr int OFF_RING = OFF_SLAB + (SLAB ? JK_KN * ROW_BYTES : 0); // [STAGES][HR][ROW_BYTES]
     static constexpr int OFF_U = OFF_RING + STAGES * STAGE_BYTES;        // double [NSP][16][NVE]
@@ -175,7 +176,11 @@ struct JKSmem {
     // shuffles -- the pass has no registers to spare, and a spilled register is an L2 round trip
     static constexpr bool RBS = NB == 2 && HM == 0;
     static constexpr int OFF_RB = (OFF_BAR + STAGES * 8 + 15) & ~15;     // RowBlock [32]
-    static constexpr int WARP_BYTES = (OFF_RB + (RBS ? 512 : 0) + 63) & ~63;
+    // (same pass) D2S: the density tile rows D2[k0 + kk, chunk] come through a two-slot cp.async ring in shared memory, one
+    // sub-row ahead: as register loads they shared a scoreboard with the first shared-memory loads of the next FMA block,
+    // which then waited for the L2 round trip
+    static constexpr int OFF_D2S = OFF_RB + (RBS ? 512 : 0);              // double2 [2][32]
+    static constexpr int WARP_BYTES = (OFF_D2S + (RBS ? 1024 : 0) + 63) & ~63;
 };
 
 // NB: rows j per row-block (4: RHF / J-only, 2: UHF).  TMA: full pieces through cp.async.bulk (false: cp.async only).
@@ -217,7 +222,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
     double *s_kout = reinterpret_cast<double *>(wbase + SM::OFF_KOUT);
     double *s_w = reinterpret_cast<double *>(wbase + SM::OFF_W);
     RowBlock *s_rb = reinterpret_cast<RowBlock *>(wbase + SM::OFF_RB);
-    constexpr bool RBS = SM::RBS;
+    constexpr bool RBS = SM::RBS, D2S = SM::RBS;
+    double2 *s_d2 = reinterpret_cast<double2 *>(wbase + SM::OFF_D2S);
+    uint32_t d2slot = 0;   // (D2S) ring slot the next iteration reads
     const uint32_t ring_u32 = smem_u32(wbase + SM::OFF_RING);
     const uint32_t bar_u32 = smem_u32(wbase + SM::OFF_BAR);
     const int n = p.n, ldd = p.ldd;
@@ -289,6 +296,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             total_it = cnt;
         }
 
+        if (D2S) cp_async_wait<0>();   // (the last look-ahead row of the previous task may still be on its way into the ring)
         // ---- producer: one piece (sub-row) per call
         int prod_rbi = -1, prod_left = 0, prod_todo = total_it * NH, prod_half = 0;   // prod_todo counts ring slots
         const char *prod_src = reinterpret_cast<const char *>(p.P);
@@ -459,8 +467,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         constexpr int D2_AHEAD = D2_TWO ? 2 : 1;
         const double *d2base = p.d2 + (size_t)(k0 + (KS ? hh : 0)) * ldd + (lane_in ? l0 : 0);
         auto load_d2 = [&](int row) { return HINT ? ldg2_keep(d2base + (size_t)row * ldd, pol_keep) : ldg2(d2base + (size_t)row * ldd); };
-        double2 d2n = load_d2(0);
-        double2 d2nn = D2_TWO ? load_d2(KSTEP) : make_double2(0.0, 0.0);
+        // (D2S: the rows go through a two-slot cp.async ring in shared memory instead, one group per row)
+        auto copy_d2 = [&](int row, uint32_t slot) {
+            cp_async16_zfill<HINT>(smem_u32(s_d2 + slot * 32 + lane), d2base + (size_t)row * ldd, 16u, pol_keep);
+            cp_async_commit();
+        };
+        double2 d2n = make_double2(0.0, 0.0), d2nn = make_double2(0.0, 0.0);
+        if (D2S) {
+            copy_d2(0, d2slot);
+        } else {
+            d2n = load_d2(0);
+            if (D2_TWO) d2nn = load_d2(KSTEP);
+        }
         fetch_rb(0);
 
         for (int rbi = 0; rbi < task.rb_count; ++rbi) {
@@ -505,15 +523,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
 
             // one ring slot: wait for the previous half-iteration in every lane (its slot is free, its shared-memory stores are
             // visible), refill the freed slot, wait for the oldest one
-            auto slot_wait = [&]() {
+            // (D2S: d2row >= 0 = density tile row to fetch for the next iteration; its group is committed BEFORE the ring
+            //  slot's, so "all but the newest three groups" = this iteration's row and ring slot are complete)
+            auto slot_wait = [&](int d2row) {
                 __syncwarp();
+                if (D2S && d2row >= 0) copy_d2(d2row, d2slot ^ 1u);
                 if (prod_todo > 0) issue_next();
                 if (full) {
+                    if (D2S) cp_async_wait<1>();
                     mbar_wait(bar_u32 + 8 * stage_r, (phase_bits >> stage_r) & 1u);
                     phase_bits ^= 1u << stage_r;
                 } else {
                     cp_async_commit();
-                    cp_async_wait<STAGES - 1>();   // this lane's 16 bytes of every row of the oldest slot have landed
+                    // this lane's 16 bytes of every row of the oldest slot have landed
+                    if (D2S)
+                        cp_async_wait<3>();
+                    else
+                        cp_async_wait<STAGES - 1>();
                 }
             };
             auto slot_ready = [&]() -> const double2 * {
@@ -526,7 +552,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
 
 #pragma unroll 2
             for (int kk = 0; kk < nit; ++kk) {   // (KS: kk counts iterations of two sub-rows, this lane's is kl)
-                slot_wait();
+                slot_wait(KSTEP * (kk + 1 < nit ? kk + 1 : 0));   // (row: D2S only; wraps into the next sweep)
                 const int kl = KS ? ((2 * kk + hh) < JK_KN ? 2 * kk + hh : JK_KN - 1) : kk;
 
                 // ---- C, loads: partials of sub-row kk-2 (buffer kk & 1; kk-1 and buffer (kk-1) & 1 in the shallow pipeline)
@@ -558,8 +584,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                         for (int e = 0; e < 4; ++e) r4[h][e] = rd[(8 * h < NV - 8 ? 8 * h : (NV > 8 ? NV - 8 : 0)) * JK_RED_STRIDE + e];
                 }
                 // ---- A: the FMA block of sub-row kk
-                const double2 d2 = d2n;
-                {
+                const double2 d2 = D2S ? s_d2[d2slot * 32 + lane] : d2n;
+                d2slot ^= 1u;
+                if (!D2S) {
                     const int ahead = kk + D2_AHEAD;   // iteration whose row is fetched now (wraps into the next sweep)
                     const double2 nx = load_d2(KSTEP * (ahead < nit ? ahead : ahead - nit));
                     d2n = D2_TWO ? d2nn : nx;
@@ -633,7 +660,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     }
                 }
                 if (NH == 2) {
-                    slot_wait();
+                    slot_wait(-1);
                     const double2 *buf1 = slot_ready();
                     fma_rows(buf1, 1);
                 }
@@ -674,7 +701,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                     }
                 }
             }
-            if (D2_TWO && nit == 1) d2n = load_d2(0);   // (one-iteration sweep: its look-ahead of two skipped the next row 0)
+            if (D2_TWO && !D2S && nit == 1) d2n = load_d2(0);   // (one-iteration sweep: its look-ahead of two skipped the next row 0)
             if (rbi + 1 < task.rb_count) fetch_rb(rbi + 1);   // in flight during the epilogue below
             {   // ---- epilogue of the row-block
             // (RBS: the row-block's scalars are re-read from shared memory here -- kept live across the sweep they were spilled)
