@@ -117,8 +117,9 @@ struct sqcc_ctx {
     int64_t native_len = 0;
     int64_t n_unique = 0;
     double eri_absmax = -1.0;    // max |stored value| (lazily computed: deterministic fixed-point mode)
-    sqcc::JKSchedule sched[5];    // [0]: 4x4 row-blocks, all tasks  [1]: 4x2 (UHF)  [2]: 4x4, 32-column chunks (spin-split UHF)
+    sqcc::JKSchedule sched[7];    // [0]: 4x4 row-blocks, all tasks  [1]: 4x2 (UHF)  [2]: 4x4, 32-column chunks (spin-split UHF)
                                   // [3]: 4x4, tasks with 48 / 64-column pieces  [4]: 4x4, narrow tasks (16 / 32 columns)
+                                  // [5], [6]: the same split of the 4x2 tasks
     int jk_variant = 0;
     int jk_cfg = 0;  // tuning knob of the streaming kernel, see jk_partial
     int jk_fixed = 0;  // deterministic mode: 64-bit fixed-point accumulation (sqcc_jk_set_deterministic)

@@ -255,6 +255,8 @@ int jk_build_schedule(sqcc_ctx *ctx)
     SQCC_TRY(build_one_schedule(ctx, ctx->sched[2], 4, 32));
     SQCC_TRY(build_one_schedule(ctx, ctx->sched[3], 4, JK_CHUNK, 1));
     SQCC_TRY(build_one_schedule(ctx, ctx->sched[4], 4, JK_CHUNK, 2));
+    SQCC_TRY(build_one_schedule(ctx, ctx->sched[5], 2, JK_CHUNK, 1));
+    SQCC_TRY(build_one_schedule(ctx, ctx->sched[6], 2, JK_CHUNK, 2));
     const size_t nl = (size_t)ctx->n * ctx->ldd;
     if (ctx->d_dwork) cudaFree(ctx->d_dwork);
     ctx->d_dwork = nullptr;
@@ -357,8 +359,9 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
     const bool uhf_split = uhf && ctx->jk_variant == 0 && ctx->jk_cfg == 6 && !ctx->jk_fixed;
     // 4 x 4 shapes, default configuration: the tasks with 48 / 64-column pieces go through the TMA kernel, the narrow ones
     // (16 / 32 columns) through the narrow-piece pass (two sub-rows per iteration, one per half-warp)
-    const bool two_pass = !uhf && ctx->jk_variant == 0 && ctx->jk_cfg == 0 && !ctx->jk_fixed;
-    const JKSchedule &sc = ctx->sched[uhf ? (uhf_split ? 2 : 1) : (two_pass ? 3 : 0)];
+    const bool two_pass = ctx->jk_variant == 0 && ctx->jk_cfg == 0 && !ctx->jk_fixed;
+    const JKSchedule &sc = ctx->sched[uhf ? (uhf_split ? 2 : (two_pass ? 5 : 1)) : (two_pass ? 3 : 0)];
+    const JKSchedule &sc_narrow = ctx->sched[uhf ? 6 : 4];
     JKParams p;
     p.P = ctx->d_eri;
     p.n = n;
@@ -398,13 +401,15 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
         ctx->launches++;
         SQCC_CUDA(cudaGetLastError());
     } else if (p.ntasks > 0 || two_pass) {
-        if (two_pass && ctx->sched[4].n_tasks > 0) {   // narrow pieces first (short tasks; the long ones fill the tail)
+        if (two_pass && sc_narrow.n_tasks > 0) {   // narrow pieces first (short tasks; the long ones fill the tail)
             JKParams pn = p;
-            pn.tasks = ctx->sched[4].d_tasks;
-            pn.rowblocks = ctx->sched[4].d_rowblocks;
-            pn.ntasks = ctx->sched[4].n_tasks;
+            pn.tasks = sc_narrow.d_tasks;
+            pn.rowblocks = sc_narrow.d_rowblocks;
+            pn.ntasks = sc_narrow.n_tasks;
             pn.counter = ctx->d_counter + 1;
-            if (!want_k)
+            if (uhf)
+                SQCC_TRY((launch_stream<2, 2, true, 8, 3, false, false, true, true, 1, 2>(ctx, pn)));
+            else if (!want_k)
                 SQCC_TRY((launch_stream<4, 1, false, 8, 2, false, false, true, true, 1, 2>(ctx, pn)));
             else
                 SQCC_TRY((launch_stream<4, 1, true, 8, 2, false, false, true, true, 1, 2>(ctx, pn)));

@@ -200,10 +200,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
     constexpr int R = SM::R, HR = SM::HR, NV = SM::NV, NVE = SM::NVE;
     static_assert(NB % NH == 0, "a ring slot holds whole j-columns of the row-block");
     static_assert(!SPIN2 || (NB == 4 && NH == 1 && !TMA && WANTK && NSPIN == 2), "spin-split pass: 4 x 4 row-blocks, cp.async ring");
-    static_assert(!KS || (NB == 4 && NH == 1 && !TMA && NS == 1), "narrow-piece pass: 4 x 4 row-blocks, cp.async ring, one density");
+    static_assert(!KS || (NH == 1 && !TMA), "narrow-piece pass: cp.async ring");
     constexpr int LW = HALF ? 16 : 32;                // double2 per ring-slot row = lanes that share one row
     constexpr int KSTEP = KS ? 2 : 1;                 // sub-rows per loop iteration
     constexpr int NVP = (NV + 7) / 8;
+    constexpr int NHV = 2 * NV;   // half-warp modes: values reduced per iteration, 16 lane partials each (16, or 24 dual-density)
+    static_assert(!HALF || NHV == 16 || NHV == 24, "half-warp reduction: one pass of 16 values, a second one of 8");
     constexpr bool DEEP = NB == 4;   // reduction pipeline over three iterations (needs NV more live registers) or two
     constexpr bool WIDE = SM::WIDE_RED;   // 32 lane partials per value in the scratch, no xor-16 fold (JKSmem)
     constexpr int RW = WIDE ? 8 : 4;      // scratch entries one lane sums per value
@@ -513,8 +515,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
             // with it every older group -- ring slots of the cp.async path -- is complete as well); the warp barrier at the
             // top of the first iteration makes them visible to all lanes
             cp_async_wait<0>();
-            constexpr int NKV = HALF ? 16 : NV;
-            constexpr int NKP = KS ? 4 : (NKV + 1) / 2;
+            constexpr int NKV = HALF ? NHV : NV;
+            constexpr int NKP = KS ? NKV / 4 : (NKV + 1) / 2;
 
             double cdp[NV];   // lane partials of the previous sub-row, published one iteration later
 #pragma unroll
@@ -572,10 +574,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                         }
                 }
                 const double2 *buf = slot_ready();
+                double rb4[4];   // (half-warp modes with 24 values: values 16 + (lane >> 2), four lanes per value, 4 entries each)
                 if (WANTK && HALF) {
-                    const double *rd = s_red + (kk & 1) * SM::RED_BUF + (lane >> 1) * JK_RED_STRIDE + (lane & 1) * 8;
+                    const double *rb = s_red + ((DEEP ? kk : kk + 1) & 1) * SM::RED_BUF;
+                    const double *rd = rb + (lane >> 1) * JK_RED_STRIDE + (lane & 1) * 8;
 #pragma unroll
                     for (int e = 0; e < 8; ++e) r8[e] = rd[e];
+                    if (NHV > 16) {
+                        const double *rd2 = rb + (16 + (lane >> 2)) * JK_RED_STRIDE + (lane & 3) * 4;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) rb4[e] = rd2[e];
+                    }
                 } else if (WANTK && !WIDE) {
                     const double *rd = s_red + ((DEEP ? kk : kk + 1) & 1) * SM::RED_BUF + red_rd_off;
 #pragma unroll
@@ -638,9 +647,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 // ---- C, arithmetic: finish sub-row kk-2 (in the first half's block when the sub-row takes two slots)
                 double csum[NVP];
                 if (WANTK && HALF) {
+                    const int kcol = DEEP ? (kk >= 2 ? kk - 2 : 16) : (kk >= 1 ? kk - 1 : 16);
                     double sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
                     sum += shfl_xor_f64(sum, 1);
-                    s_kout[(lane >> 1) * JK_RED_STRIDE + (kk >= 2 ? kk - 2 : 16)] = sum;   // both lanes of the pair: same value
+                    s_kout[(lane >> 1) * JK_RED_STRIDE + kcol] = sum;   // both lanes of the pair: same value
+                    if (NHV > 16) {
+                        double sb = (rb4[0] + rb4[1]) + (rb4[2] + rb4[3]);
+                        sb += shfl_xor_f64(sb, 1);
+                        sb += shfl_xor_f64(sb, 2);
+                        s_kout[(16 + (lane >> 2)) * JK_RED_STRIDE + kcol] = sb;
+                    }
                 } else if (WANTK) {
 #pragma unroll
                     for (int h = 0; h < NVP; ++h) {
@@ -734,10 +750,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
                 for (int d = DEEP ? 0 : 1; d < 2; ++d) {   // d = 0: iteration nit-2 (buffer nit & 1), d = 1: iteration nit-1
                     const int ks = nit - 2 + d;
                     if (HALF) {
-                        const double *rd = s_red + ((nit + d) & 1) * SM::RED_BUF + (lane >> 1) * JK_RED_STRIDE + (lane & 1) * 8;
+                        const double *rb = s_red + ((nit + d) & 1) * SM::RED_BUF;
+                        const double *rd = rb + (lane >> 1) * JK_RED_STRIDE + (lane & 1) * 8;
                         double sum = ((rd[0] + rd[1]) + (rd[2] + rd[3])) + ((rd[4] + rd[5]) + (rd[6] + rd[7]));
                         sum += shfl_xor_f64(sum, 1);
                         if ((lane & 1) == 0 && ks >= 0) s_kout[(lane >> 1) * JK_RED_STRIDE + ks] = sum;
+                        if (NHV > 16) {
+                            const double *rd2 = rb + (16 + (lane >> 2)) * JK_RED_STRIDE + (lane & 3) * 4;
+                            double sb = (rd2[0] + rd2[1]) + (rd2[2] + rd2[3]);
+                            sb += shfl_xor_f64(sb, 1);
+                            sb += shfl_xor_f64(sb, 2);
+                            if ((lane & 3) == 0 && ks >= 0) s_kout[(16 + (lane >> 2)) * JK_RED_STRIDE + ks] = sb;
+                        }
                         continue;
                     }
                     const double *rd = s_red + (WIDE ? 0 : ((nit + d) & 1) * SM::RED_BUF) + red_rd_off;
@@ -768,10 +792,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
 #pragma unroll
                 for (int m = 0; m < NKP; ++m) {
                     const int qv = KS ? 4 * m + (lane >> 3) : 2 * m + (lane >> 4);
-                    const int q = HALF ? (qv & 7) : qv;
-                    const int s = SPIN2 ? (qv >> 3) : (KS ? 0 : q / (NI + NB)), wq = q % (NI + NB);
+                    const int q = HALF ? qv % NV : qv, par = HALF ? qv / NV : 0;   // par: spin (SPIN2) / sub-row parity (KS)
+                    const int s = SPIN2 ? par : q / (NI + NB), wq = q % (NI + NB);
                     const int row = wq < NI ? i0 + wq : j0 + (wq - NI);
-                    const int kkq = KS ? 2 * (lane & 7) + (qv >> 3) : (lane & 15);
+                    const int kkq = KS ? 2 * (lane & 7) + par : (lane & 15);
                     const bool ok = qv < NKV && row >= 0 && row < n && kkq < nkk;
                     const double v = qv < NKV ? s_kout[qv * JK_RED_STRIDE + (KS ? (lane & 7) : (lane & 15))] : 0.0;
                     flush_add<FIXED>(ok, p.kt + (ok ? s * nl + (size_t)row * ldd + k0 + kkq : 0), v, fx);
