@@ -269,13 +269,13 @@ int jk_build_schedule(sqcc_ctx *ctx)
     return SQCC_OK;
 }
 
-template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, bool SLAB, int NH, int HM = 0>
+template <int NB, int NSPIN, bool WANTK, int WARPS, int STAGES, bool TMA, bool FIXED, bool HINT, int HM = 0>
 static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
 {
-    using SM = JKSmem<NB, (WANTK && HM != 1) ? NSPIN : 1, STAGES, SLAB, NH, HM>;
+    using SM = JKSmem<NB, (WANTK && HM != 1) ? NSPIN : 1, STAGES, HM>;
     const size_t smem = (size_t)WARPS * SM::WARP_BYTES;
     static_assert((size_t)WARPS * SM::WARP_BYTES <= 232448, "shared memory per CTA");
-    auto kern = jk_stream_kernel<NB, NSPIN, WANTK, WARPS, STAGES, TMA, FIXED, HINT, SLAB, NH, HM>;
+    auto kern = jk_stream_kernel<NB, NSPIN, WANTK, WARPS, STAGES, TMA, FIXED, HINT, HM>;
     SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = ctx->sm_count;
     int max_useful = (p.ntasks + WARPS - 1) / WARPS;
@@ -287,22 +287,19 @@ static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
     return SQCC_OK;
 }
 
-// STAGES counts ring slots of whole pieces (R rows).  cfg 4 runs the 4 x 4 shapes with half-piece slots instead (NH = 2:
-// 4 x 4 KB, a slot is handed back as soon as its 8 rows are consumed): more bytes in flight from the same 16 KB, but the
-// second producer / wait step per sub-row costs more than it gains (-12 % RHF, profiles/r02_perf_ab_halfslots.log).
+// STAGES counts ring slots (the R rows of one iteration + their density tile row).
 template <int NB, int NSPIN, bool WANTK, int STAGES>
 static int launch_stream_cfg(sqcc_ctx *ctx, const JKParams &p)
 {
-    // cfg 0: TMA ring, L2 cache-policy hints, J~ slab (default; the 4 x 4 shapes add the narrow-piece pass, see jk_partial)
-    //     1: cp.async ring for every piece (A/B of the TMA path)   2: no L2 hints   3: no J~ slab, one more ring stage
-    //     4: half-piece ring slots (4 x 4 shapes)   6: spin-split UHF   7: one pass over all tasks (no narrow-piece pass)
-    if (ctx->jk_fixed) return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, true, true, true, 1>(ctx, p);
+    // cfg 0: TMA ring, L2 cache-policy hints (default; adds the narrow-piece pass, see jk_partial)
+    //     1: cp.async ring for every piece (A/B of the TMA path)   2: no L2 hints
+    //     6: spin-split UHF   7: one pass over all tasks (no narrow-piece pass)
+    // (retired after their A/B, logs in profiles/: 3 = no J~ slab + one more ring stage, 4 = half-piece ring slots)
+    if (ctx->jk_fixed) return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, true, true>(ctx, p);
     switch (ctx->jk_cfg) {
-    case 1: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, false, false, true, true, 1>(ctx, p);
-    case 2: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, false, true, 1>(ctx, p);
-    case 3: return launch_stream<NB, NSPIN, WANTK, 8, STAGES + 1, true, false, true, false, 1>(ctx, p);
-    case 4: return launch_stream<NB, NSPIN, WANTK, 8, (NB == 4 ? 2 * STAGES : STAGES), true, false, true, true, (NB == 4 ? 2 : 1)>(ctx, p);
-    default: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, true, true, 1>(ctx, p);
+    case 1: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, false, false, true>(ctx, p);
+    case 2: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, false>(ctx, p);
+    default: return launch_stream<NB, NSPIN, WANTK, 8, STAGES, true, false, true>(ctx, p);
     }
 }
 
@@ -408,14 +405,14 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
             pn.ntasks = sc_narrow.n_tasks;
             pn.counter = ctx->d_counter + 1;
             if (uhf)
-                SQCC_TRY((launch_stream<2, 2, true, 8, 3, false, false, true, true, 1, 2>(ctx, pn)));
+                SQCC_TRY((launch_stream<2, 2, true, 8, 3, false, false, true, 2>(ctx, pn)));
             else if (!want_k)
-                SQCC_TRY((launch_stream<4, 1, false, 8, 2, false, false, true, true, 1, 2>(ctx, pn)));
+                SQCC_TRY((launch_stream<4, 1, false, 8, 2, false, false, true, 2>(ctx, pn)));
             else
-                SQCC_TRY((launch_stream<4, 1, true, 8, 2, false, false, true, true, 1, 2>(ctx, pn)));
+                SQCC_TRY((launch_stream<4, 1, true, 8, 2, false, false, true, 2>(ctx, pn)));
         }
         if (uhf_split)
-            SQCC_TRY((launch_stream<4, 2, true, 8, 3, false, false, true, true, 1, 1>(ctx, p)));
+            SQCC_TRY((launch_stream<4, 2, true, 8, 3, false, false, true, 1>(ctx, p)));
         else if (uhf)
             SQCC_TRY((launch_stream_cfg<2, 2, true, 3>(ctx, p)));
         else if (p.ntasks == 0)
