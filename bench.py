@@ -483,6 +483,23 @@ def extras(eng, torch):
     res["lda_uks_G354200_N62"] = {"rho_ms": float(rho_ms), "vxc_ms": float(vxc_ms),
                                   "rho_tflops": fl / (rho_ms * 1e-3) / 1e12, "vxc_tflops": fl / (vxc_ms * 1e-3) / 1e12,
                                   "vxc_frac_of_dgemm": fl / (vxc_ms * 1e-3) / 1e12 / peak}
+    # the generic path (N > 64: pipelined DMMA GEMM with row-dot / symmetric split-K epilogues) at benzene def2-TZVP size
+    g, n = 200000, 222
+    phi = rng.standard_normal((g, n)) * np.exp(-rng.uniform(0, 8, size=(g, 1)))
+    eng.attach_grid(phi, rng.uniform(0, 1e-2, size=g))
+    d = density_rhf(n, 21, 5)
+    ts = []
+    for it in range(5):
+        eng.lda_vxc(d)
+        tm = eng.timings()
+        if it >= 2:
+            ts.append((tm["rho"], tm["vxc"]))
+    rho_ms, vxc_ms = np.mean(ts, axis=0)
+    fl = 2.0 * g * n * n
+    res["lda_rks_G200000_N222"] = {"rho_ms": float(rho_ms), "vxc_ms": float(vxc_ms),
+                                   "rho_tflops": fl / (rho_ms * 1e-3) / 1e12,
+                                   "vxc_tflops_reference_equivalent": fl / (vxc_ms * 1e-3) / 1e12,
+                                   "note": "V_xc computes the tiles on and above the diagonal only (symmetric)"}
     n, no = 222, 21
     eng.attach_eri_synth(n, SEED)
     q, _ = np.linalg.qr(rng.standard_normal((n, n)))

@@ -108,8 +108,7 @@ int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, doubl
 int sqcc_jk_build_host(sqcc_ctx *ctx, const double *h_D, int nspin, int want_k, double *h_J, double *h_K);
 /* Select the kernel: 0 = streaming warp-task kernel, TMA ring + narrow-piece pass (default), 1 = simple atomics kernel
  * (cross-check), 16+c = streaming kernel, tuning configuration c kept for A/B measurements (1: cp.async ring instead of
- * TMA, 2: no L2 cache-policy hints, 3: no J~ slab / one more ring stage, 4: half-piece ring slots, 6: spin-split UHF
- * pass, 7: one pass over all tasks). */
+ * TMA, 2: no L2 cache-policy hints, 6: spin-split UHF pass, 7: one pass over all tasks; other values = default). */
 int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant);
 /* Deterministic mode (on != 0): every flush of a partial sum into the J~/K~ work matrices is converted to 64-bit fixed
  * point and added with an INTEGER atomic (associative), so J and K are bit-for-bit reproducible from run to run, under

@@ -164,10 +164,12 @@ __device__ __forceinline__ void cp_async8_zfill(double *smem_dst, const double *
 template <int WM, int WN, int MT, int PSTAGES, int BK>
 constexpr int gemm_pipe_smem_bytes()
 {
-    return PSTAGES * BK * ((8 * MT * WM + 4) + (32 * WN + 4)) * (int)sizeof(double);
+    return PSTAGES * BK * ((8 * MT * WM + 4) + (32 * WN + 4) + 1) * (int)sizeof(double);
 }
 
-template <bool A_MFAST, int BMODE, int WM, int WN, int MT, int PSTAGES, int BK>
+// EPI / SCALE (the grid quadrature for N > 64): EPI_ATOMIC = split-K partial sums (blockIdx.z = batch * splitk + split) with
+// the per-k scale w v folded into the A fragments; EPI_ROWDOT = out[m] += sum_n acc[m,n] X[m,n] (rho on the grid).
+template <bool A_MFAST, int BMODE, int WM, int WN, int MT, int PSTAGES, int BK, int EPI = EPI_STORE, bool SCALE = false>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmArgs g)
 {
     static_assert(WM * WN == 4, "four warps");
@@ -177,18 +179,28 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmA
     extern __shared__ __align__(128) double gemm_sm[];
     double *As = gemm_sm;                                      // [PSTAGES][BK][LDA_S]
     double *Bs = gemm_sm + PSTAGES * BK * LDA_S;           // [PSTAGES][BK][LDB_S]
+    double *Ss = Bs + PSTAGES * BK * LDB_S;                // [PSTAGES][BK] per-k scale
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp / WN) * (8 * MT), wn = (warp % WN) * 32;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int bz = blockIdx.z;
+    if (EPI == EPI_ATOMIC && BM == BN && g.symmetric && blockIdx.x < blockIdx.y) return;   // mirrored by the tile (y, x)
+    const bool mirror = EPI == EPI_ATOMIC && BM == BN && g.symmetric && blockIdx.x != blockIdx.y;
+    const int bz = EPI == EPI_STORE ? blockIdx.z : blockIdx.z / g.splitk;
+    const int sz = EPI == EPI_STORE ? 0 : blockIdx.z % g.splitk;
     const double *A = g.A + (int64_t)bz * g.batch_a;
     const double *B = g.B + (int64_t)bz * g.batch_b;
+    const double *scale = SCALE ? g.scale + (int64_t)bz * g.batch_scale : nullptr;
     const int64_t *koff = BMODE == B_KOFF ? g.koff + (int64_t)bz * g.batch_koff : nullptr;
-    const int ktiles = (g.K + BK - 1) / BK;
+    // k-tiles of this CTA (split-K: contiguous ranges of whole tiles)
+    const int ktiles_all = (g.K + BK - 1) / BK;
+    const int per = EPI == EPI_STORE ? ktiles_all : (ktiles_all + g.splitk - 1) / g.splitk;
+    const int kt_lo = sz * per;
+    const int ktiles = kt_lo + per < ktiles_all ? per : (ktiles_all > kt_lo ? ktiles_all - kt_lo : 0);
 
     auto issue_tile = [&](int kt, int stage) {
-        const int kbase = kt * BK;
+        const int kbase = (kt_lo + kt) * BK;
         double *as = As + stage * BK * LDA_S, *bs = Bs + stage * BK * LDB_S;
+        if (SCALE && tid < BK) cp_async8_zfill(Ss + stage * BK + tid, kbase + tid < g.K ? scale + kbase + tid : scale, kbase + tid < g.K);
 #pragma unroll
         for (int e = 0; e < EA; ++e) {
             const int idx = tid + e * GEMM_THREADS;
@@ -238,6 +250,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmA
         if (kt + PSTAGES - 1 < ktiles) issue_tile(kt + PSTAGES - 1, (kt + PSTAGES - 1) % PSTAGES);
         asm volatile("cp.async.commit_group;" ::: "memory");
         const double *as = As + (kt % PSTAGES) * BK * LDA_S, *bs = Bs + (kt % PSTAGES) * BK * LDB_S;
+        const double *ss = Ss + (kt % PSTAGES) * BK;
 #pragma unroll
         for (int ks = 0; ks < BK; ks += 4) {
             double af[MT], bf[4];
@@ -245,6 +258,11 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmA
             for (int i = 0; i < MT; ++i) af[i] = as[(ks + (lane & 3)) * LDA_S + wm + i * 8 + (lane >> 2)];
 #pragma unroll
             for (int j = 0; j < 4; ++j) bf[j] = bs[(ks + (lane & 3)) * LDB_S + wn + j * 8 + (lane >> 2)];
+            if (SCALE) {   // the B fragment is the cheaper side to scale (4 values per lane against MT)
+                const double sc = ss[ks + (lane & 3)];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] *= sc;
+            }
 #pragma unroll
             for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -254,32 +272,62 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmA
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     double *C = g.C + (int64_t)bz * g.batch_c;
+    if (EPI == EPI_ROWDOT) {
+        // out[m] += sum_n acc[m,n] X[m,n]: the lane's columns, then the four lanes of a quad, one atomic per row and warp
 #pragma unroll
-    for (int i = 0; i < MT; ++i) {
-        const int gm = m0 + wm + i * 8 + (lane >> 2);
-        if (gm >= g.M) continue;
+        for (int i = 0; i < MT; ++i) {
+            const int gm = m0 + wm + i * 8 + (lane >> 2);
+            double part = 0.0;
+            if (gm < g.M) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + wn + j * 8 + 2 * (lane & 3);
-            double *dst = C + (int64_t)gm * g.sc_m + gn;
-            if (gn < g.N) dst[0] = acc[i][j][0];
-            if (gn + 1 < g.N) dst[1] = acc[i][j][1];
+                for (int j = 0; j < 4; ++j) {
+                    const int gn = n0 + wn + j * 8 + 2 * (lane & 3);
+                    const double *x = g.X + (int64_t)gm * g.sc_m + gn;
+                    if (gn < g.N) part = fma(acc[i][j][0], __ldg(x), part);
+                    if (gn + 1 < g.N) part = fma(acc[i][j][1], __ldg(x + 1), part);
+                }
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if ((lane & 3) == 0 && gm < g.M) atomicAdd(C + gm, part);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int gm = m0 + wm + i * 8 + (lane >> 2);
+            if (gm >= g.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int gn = n0 + wn + j * 8 + 2 * (lane & 3);
+                double *dst = C + (int64_t)gm * g.sc_m + gn;
+                if (EPI == EPI_ATOMIC) {
+                    if (gn < g.N) atomicAdd(dst, acc[i][j][0]);
+                    if (gn + 1 < g.N) atomicAdd(dst + 1, acc[i][j][1]);
+                    if (mirror) {
+                        if (gn < g.N) atomicAdd(C + (int64_t)gn * g.sc_m + gm, acc[i][j][0]);
+                        if (gn + 1 < g.N) atomicAdd(C + (int64_t)(gn + 1) * g.sc_m + gm, acc[i][j][1]);
+                    }
+                } else {
+                    if (gn < g.N) dst[0] = acc[i][j][0];
+                    if (gn + 1 < g.N) dst[1] = acc[i][j][1];
+                }
+            }
         }
     }
 }
 
-template <bool MF, int BMD, int WM, int WN, int MT, int PSTAGES, int BK>
+template <bool MF, int BMD, int WM, int WN, int MT, int PSTAGES, int BK, int EPI = EPI_STORE, bool SCALE = false>
 inline int gemm_pipe_launch_st(sqcc_ctx *ctx, const GemmArgs &g)
 {
     constexpr int BM = 8 * MT * WM, BN = 32 * WN;
     constexpr int smem = gemm_pipe_smem_bytes<WM, WN, MT, PSTAGES, BK>();
-    auto kern = gemm_f64_pipe_kernel<MF, BMD, WM, WN, MT, PSTAGES, BK>;
+    auto kern = gemm_f64_pipe_kernel<MF, BMD, WM, WN, MT, PSTAGES, BK, EPI, SCALE>;
     static bool attr_done = false;   // one attribute call per instantiation
     if (!attr_done) {
         SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch);
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch * (EPI == EPI_STORE ? 1 : g.splitk));
     SQCC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "GEMM grid too large");
     kern<<<grid, GEMM_THREADS, smem, ctx->stream>>>(g);
     ctx->launches++;
@@ -327,6 +375,11 @@ int gemm_f64(sqcc_ctx *ctx, const GemmArgs &g, int epi, int bmode)
     SQCC_REQUIRE(epi != EPI_STORE || g.splitk == 1, "split-K needs an accumulating epilogue");
     if (epi == EPI_STORE && !g.scale) return gemm_f64_store(ctx, g, bmode);
     const bool mfast = g.sa_m == 1 && g.sa_k != 1;
+    // the grid quadrature (generic N): pipelined kernel, 64 x 64 tiles, three ring stages (K is long or the grid is huge)
+    if (bmode == B_ROWS && epi == EPI_ATOMIC && g.scale && mfast)
+        return gemm_pipe_launch_st<true, B_ROWS, 2, 2, 4, 3, 16, EPI_ATOMIC, true>(ctx, g);
+    if (bmode == B_ROWS && epi == EPI_ROWDOT && !g.scale && !mfast)
+        return gemm_pipe_launch_st<false, B_ROWS, 2, 2, 4, 3, 16, EPI_ROWDOT, false>(ctx, g);
     const bool small_m = g.M <= 32 && mfast && epi == EPI_STORE;
     SQCC_REQUIRE(bmode == B_ROWS || (mfast && epi == EPI_STORE), "packed B operands need the A^T / STORE form");
     const int bm = small_m ? 32 : 64;

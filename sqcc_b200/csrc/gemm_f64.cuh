@@ -41,6 +41,8 @@ struct GemmArgs {
     int batch;            // blockIdx.z = batch * splitk + split
     int64_t batch_a, batch_b, batch_c, batch_scale, batch_koff;
     int splitk;           // K is cut into `splitk` contiguous ranges (EPI_ATOMIC / EPI_ROWDOT only)
+    int symmetric;        // EPI_ATOMIC, M == N, A == B^T: only the tiles on and above the diagonal are computed and their
+                          // sums added to both triangles (the grid quadrature phi^T diag(w v) phi)
 };
 
 constexpr int GEMM_BN = 64, GEMM_BK = 16, GEMM_THREADS = 128;

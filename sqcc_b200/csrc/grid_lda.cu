@@ -105,8 +105,10 @@ static int vxc_gemm(sqcc_ctx *ctx, const double *d_wv, int nspin, double *d_V)
     g.batch_b = 0;
     g.batch_c = (int64_t)n * n;
     g.batch_scale = ctx->G;
-    // enough k-splits to fill the machine ~2x with 64x64 output blocks
-    int blocks = ((n + 63) / 64) * ((n + 63) / 64) * nspin;
+    g.symmetric = 1;   // phi^T diag(w v) phi: tiles on and above the diagonal, mirrored in the epilogue
+    // enough k-splits to fill the machine ~2x with the computed 64x64 output blocks
+    const int nt = (n + 63) / 64;
+    int blocks = nt * (nt + 1) / 2 * nspin;
     int splitk = (2 * ctx->sm_count * 4 + blocks - 1) / blocks;
     int ktiles = (int)((ctx->G + GEMM_BK - 1) / GEMM_BK);
     if (splitk > ktiles) splitk = ktiles;
