@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_pipe_kernel(const GemmA
     const double *scale = SCALE ? g.scale + (int64_t)bz * g.batch_scale : nullptr;
     const int64_t *koff = BMODE == B_KOFF ? g.koff + (int64_t)bz * g.batch_koff : nullptr;
     // k-tiles of this CTA (split-K: contiguous ranges of whole tiles)
-    const int ktiles_all = (g.K + BK - 1) / BK;
+    const int Keff = g.ktri && n0 + BN < g.K ? n0 + BN : g.K;
+    const int ktiles_all = (Keff + BK - 1) / BK;
     const int per = EPI == EPI_STORE ? ktiles_all : (ktiles_all + g.splitk - 1) / g.splitk;
     const int kt_lo = sz * per;
     const int ktiles = kt_lo + per < ktiles_all ? per : (ktiles_all > kt_lo ? ktiles_all - kt_lo : 0);

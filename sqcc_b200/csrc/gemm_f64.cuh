@@ -43,6 +43,7 @@ struct GemmArgs {
     int splitk;           // K is cut into `splitk` contiguous ranges (EPI_ATOMIC / EPI_ROWDOT only)
     int symmetric;        // EPI_ATOMIC, M == N, A == B^T: only the tiles on and above the diagonal are computed and their
                           // sums added to both triangles (the grid quadrature phi^T diag(w v) phi)
+    int ktri;             // B is upper triangular (B(k,n) = 0 for k > n): a column block only runs over k < n0 + BN
 };
 
 constexpr int GEMM_BN = 64, GEMM_BK = 16, GEMM_THREADS = 128;

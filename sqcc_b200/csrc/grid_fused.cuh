@@ -51,9 +51,12 @@ grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w
     // zero everything once (pad columns / rows must stay finite), then stage D
     for (int e = tid; e < NSPIN * 64 * GF_LD + 2 * GF_TM * GF_LD; e += GF_WARPS * 32) gsm[e] = 0.0;
     __syncthreads();
+    // rho_p = sum_mn phi_pm D_mn phi_pn = sum_{m <= n} phi_pm U_mn phi_pn with the upper-triangular U_mn = D_mn + D_nm
+    // (m < n), U_mm = D_mm: the product T = phi U needs only the k-steps with k <= n of every column tile -- 72 of the 128
+    // (k-step, column tile) pairs at N = 64 -- and is exact for any D, symmetric or not.
     for (int e = tid; e < NSPIN * n * n; e += GF_WARPS * 32) {
         const int s = e / (n * n), r = (e / n) % n, c = e % n;
-        Ds[(s * 64 + r) * GF_LD + c] = D[e];
+        Ds[(s * 64 + r) * GF_LD + c] = r < c ? D[e] + D[(size_t)s * n * n + (size_t)c * n + r] : (r == c ? D[e] : 0.0);
     }
     const int64_t ntiles = (G + GF_TM - 1) / GF_TM;
     const int ksteps = (n + 3) >> 2;
@@ -79,16 +82,22 @@ grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
             const double *B = Ds + s * 64 * GF_LD;
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const int kq = 4 * ks + (lane & 3);
-                const double a0 = A[(lane >> 2) * GF_LD + kq], a1 = A[(8 + (lane >> 2)) * GF_LD + kq];
-                double b[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) b[j] = B[kq * GF_LD + 8 * j + (lane >> 2)];
+            for (int jm = 0; jm < 8; ++jm) {       // k-steps 2 jm, 2 jm + 1 (rows 8 jm .. 8 jm + 7 of U) meet column tiles j >= jm
+                if (2 * jm >= ksteps) break;       // (warp-uniform)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, b[j]);
-                    dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, b[j]);
+                for (int h = 0; h < 2; ++h) {
+                    const int ks = 2 * jm + h;
+                    if (ks >= ksteps) break;
+                    const int kq = 4 * ks + (lane & 3);
+                    const double a0 = A[(lane >> 2) * GF_LD + kq], a1 = A[(8 + (lane >> 2)) * GF_LD + kq];
+#pragma unroll
+                    for (int j = jm; j < 8; ++j) {
+                        if (8 * j >= n) break;     // column tiles past the basis
+                        const double b = B[kq * GF_LD + 8 * j + (lane >> 2)];
+                        dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, b);
+                        dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, b);
+                    }
                 }
             }
             // rho = rowdot(T, phi): lane holds T[row = lane/4 (+8)][col = 8j + 2(lane%4) + {0,1}]
@@ -147,14 +156,23 @@ grid_vxc_kernel(const double *__restrict__ phi, const double *__restrict__ wv, i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int e = tid; e < 2 * TMV * GF_LD + 2 * NSPIN * TMV; e += GF_WARPS * 32) gsm[e] = 0.0;
     const int64_t ntiles = (G + TMV - 1) / TMV;
-    const int pt0 = 2 * (warp >> 1), qt0 = 4 * (warp & 1);   // this warp's 2 p-tiles x 4 q-tiles of the 64 x 64 output
-    double acc[NSPIN][2][4][2];
+    // V is symmetric: only the 36 m8n8 tiles (pt <= qt) of the 64 x 64 output are computed (the flush mirrors them).  Rows
+    // r and 7 - r hold 9 of them; warp 2r takes (r, r .. r+4), warp 2r + 1 the other 3 - r tiles of row r and the r + 1
+    // tiles of row 7 - r: five / four DMMAs per k-step and warp instead of eight, one A fragment per row, and the two
+    // warps of a scheduler (w, w + 4) carry 5 + 4 tiles.
+    const int wr = warp >> 1, second = warp & 1;
+    const int prow0 = wr, prow1 = second ? 7 - wr : wr;   // p-tile of the first `nfirst` tiles / of the rest
+    const int nfirst = second ? 3 - wr : 5;
+    const int ntile = second ? 4 : 5;
+    int qt[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) qt[i] = !second ? wr + i : (i < nfirst ? wr + 5 + i : (7 - wr) + (i - nfirst));
+    if (second) qt[4] = qt[3];   // (unused slot: any valid column)
+    double acc[NSPIN][5][2];
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s)
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[s][i][j][0] = acc[s][i][j][1] = 0.0;
+        for (int i = 0; i < 5; ++i) acc[s][i][0] = acc[s][i][1] = 0.0;
     auto load_w = [&](int b, int64_t t) {
         for (int e = tid; e < NSPIN * TMV; e += GF_WARPS * 32) {
             const int s = e / TMV, r = e % TMV;
@@ -185,38 +203,40 @@ grid_vxc_kernel(const double *__restrict__ phi, const double *__restrict__ wv, i
         for (int ks = 0; ks < TMV / 4; ++ks) {
             const int gq = 4 * ks + (lane & 3);           // grid point (k index) of this lane's fragment element
             const double *row = A + gq * GF_LD + (lane >> 2);
-            double fa[2], fb[4];
+            double fb[5];
+            const double fa0 = row[8 * prow0], fa1 = row[8 * prow1];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) fa[i] = row[8 * (pt0 + i)];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) fb[j] = row[8 * (qt0 + j)];
+            for (int i = 0; i < 5; ++i) fb[i] = row[8 * qt[i]];
 #pragma unroll
             for (int s = 0; s < NSPIN; ++s) {
                 const double sc = Wt[s * TMV + gq];
+                const double a0 = fa0 * sc, a1 = fa1 * sc;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const double a = fa[i] * sc;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[s][i][j][0], acc[s][i][j][1], a, fb[j]);
-                }
+                for (int i = 0; i < 4; ++i) dmma_m8n8k4(acc[s][i][0], acc[s][i][1], i < nfirst ? a0 : a1, fb[i]);
+                if (!second) dmma_m8n8k4(acc[s][4][0], acc[s][4][1], a0, fb[4]);   // (warp-uniform branch)
             }
         }
         buf ^= 1;
     }
-    // flush the CTA's partial: lane holds V[p = 8 pt + lane/4][q = 8 qt + 2(lane%4) + {0,1}]
+    // flush the CTA's partial: lane holds V[p = 8 pt + lane/4][q = 8 qt + 2(lane%4) + {0,1}]; tiles above the diagonal
+    // go to both triangles
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s)
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int pr = 8 * (pt0 + i) + (lane >> 2), q = 8 * (qt0 + j) + 2 * (lane & 3);
-                if (pr < n) {
-                    double *dst = V + (size_t)s * n * n + (size_t)pr * n + q;
-                    if (q < n) atomicAdd(dst, acc[s][i][j][0]);
-                    if (q + 1 < n) atomicAdd(dst + 1, acc[s][i][j][1]);
+        for (int i = 0; i < 5; ++i) {
+            if (i >= ntile) continue;
+            const int pt = i < nfirst ? prow0 : prow1;
+            const int pr = 8 * pt + (lane >> 2), q = 8 * qt[i] + 2 * (lane & 3);
+            double *Vs = V + (size_t)s * n * n;
+            if (pr < n) {
+                if (q < n) atomicAdd(Vs + (size_t)pr * n + q, acc[s][i][0]);
+                if (q + 1 < n) atomicAdd(Vs + (size_t)pr * n + q + 1, acc[s][i][1]);
+                if (pt != qt[i]) {
+                    if (q < n) atomicAdd(Vs + (size_t)q * n + pr, acc[s][i][0]);
+                    if (q + 1 < n) atomicAdd(Vs + (size_t)(q + 1) * n + pr, acc[s][i][1]);
                 }
             }
+        }
 }
 
 inline bool grid_fused_ok(const sqcc_ctx *ctx)

@@ -57,13 +57,30 @@ __global__ void mul_kernel(const double *a, const double *b, int64_t n, double *
         o[i] = a[i] * b[i];
 }
 
+// U_mn = D_mn + D_nm (m < n), U_mm = D_mm, 0 below the diagonal: rho_p = sum_{m <= n} phi_pm U_mn phi_pn for any D
+__global__ void upper_fold_kernel(const double *__restrict__ D, int nspin, int n, double *__restrict__ U)
+{
+    const int64_t tot = (int64_t)nspin * n * n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = e / ((int64_t)n * n);
+        const int r = (int)((e / n) % n), c = (int)(e % n);
+        U[e] = r < c ? D[e] + D[s * n * n + (int64_t)c * n + r] : (r == c ? D[e] : 0.0);
+    }
+}
+
 static int rho_gemm(sqcc_ctx *ctx, const double *d_D, int nspin, double *d_rho)
 {
     const int n = ctx->grid_n;
     SQCC_CUDA(cudaMemsetAsync(d_rho, 0, sizeof(double) * nspin * ctx->G, ctx->stream));
+    // triangular form: a 64-column block of T = phi U only needs the k-tiles with k < its last column
+    double *U = ctx->d_gridwork + 4 * ctx->G;
+    upper_fold_kernel<<<(unsigned)(((int64_t)nspin * n * n + 255) / 256), 256, 0, ctx->stream>>>(d_D, nspin, n, U);
+    ctx->launches++;
+    SQCC_CUDA(cudaGetLastError());
     GemmArgs g{};
+    g.ktri = 1;
     g.A = ctx->d_phi;
-    g.B = d_D;
+    g.B = U;
     g.C = d_rho;
     g.X = ctx->d_phi;
     g.scale = nullptr;
@@ -121,6 +138,7 @@ static int vxc_gemm(sqcc_ctx *ctx, const double *d_wv, int nspin, double *d_V)
 int grid_rho(sqcc_ctx *ctx, const double *d_D, double *d_rho)
 {
     SQCC_REQUIRE(ctx->G < (int64_t)1 << 31, "grid too large");
+    SQCC_TRY(ensure_gridwork(ctx, sizeof(double) * (4 * ctx->G + 2 * (size_t)ctx->grid_n * ctx->grid_n)));
     return rho_gemm(ctx, d_D, 1, d_rho);
 }
 
@@ -143,7 +161,7 @@ int lda_vxc(sqcc_ctx *ctx, const double *d_D, int nspin, double *d_Vxc, double *
 {
     SQCC_REQUIRE(ctx->G < (int64_t)1 << 31, "grid too large");
     const int64_t G = ctx->G;
-    SQCC_TRY(ensure_gridwork(ctx, sizeof(double) * 4 * G));
+    SQCC_TRY(ensure_gridwork(ctx, sizeof(double) * (4 * G + 2 * (size_t)ctx->grid_n * ctx->grid_n)));
     double *rho = d_rho ? d_rho : ctx->d_gridwork;  // [nspin][G]
     double *wv = ctx->d_gridwork + 2 * G;           // [nspin][G]
     // constants exactly as ksdft_functional.py:59, :89, :125, :173 evaluate them
