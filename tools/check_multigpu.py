@@ -1,6 +1,7 @@
 """Multi-process correctness check of the fused peer-memory exchange (CUDA IPC path):
 torchrun --nproc-per-node W tools/check_multigpu.py   -- every rank must end with the oracle's J/K, bit-identical
-across ranks, for RHF / UHF / J-only, repeated builds and re-attached tensors; the NCCL path must agree to 1e-11."""
+across ranks, for RHF / UHF / J-only, repeated builds and re-attached tensors; the NCCL path must agree to 1e-11; the
+deterministic mode must be bit-reproducible and identical on all ranks."""
 import os
 import sys
 
@@ -37,6 +38,20 @@ for n, seed in ((70, 5), (37, 9), (130, 2)):
         j2, k2 = eng.jk(d, want_k=kind != "jonly")
         worst = max(worst, np.abs(j2 - jr).max(), 0.0 if k2 is None else np.abs(k2 - kr).max())
         eng.set_exchange("p2p")
+    # deterministic mode (64-bit fixed-point accumulation, integer sums across the ranks): two builds bit-identical,
+    # every rank identical, still within the parity gate
+    eng.set_deterministic(True)
+    d = synth.synth_density_uhf(n, n // 3, n // 4, 3)
+    jr, kr = cjk.jk_packed(packed, n, d)
+    ja, ka = eng.jk(d)
+    jb, kb = eng.jk(d)
+    assert np.array_equal(ja, jb) and np.array_equal(ka, kb), f"rank {rank}: deterministic mode not reproducible"
+    worst = max(worst, np.abs(ja - jr).max(), np.abs(ka - kr).max())
+    t = torch.from_numpy(np.concatenate([ja.ravel(), ka.ravel()])).to(eng.device)
+    ref = t.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(t, ref), f"rank {rank}: deterministic result differs from rank 0"
+    eng.set_deterministic(False)
     # device-resident SCF step on the sharded tensor (replicated linear algebra, fused exchange inside)
     h = np.diag(-np.arange(1.0, n + 1.0))
     eng.scf_setup(h, np.eye(n), 1, n // 4, n // 4, False)
