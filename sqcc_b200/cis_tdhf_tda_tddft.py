@@ -27,6 +27,9 @@ class Calculator:
         n_virt = c_virt.shape[1]
         engine = getattr(scf, "engine", None)
         if engine is None:
+            if getattr(scf, "ao_electron_repulsion_integral", None) is None:
+                raise RuntimeError("the SCF object carries neither an engine nor the AO ERI tensor "
+                                   "(direct_ingest on several ranks keeps only shards): nothing to transform")
             engine = FockEngine()
             engine.attach_eri_full(scf.ao_electron_repulsion_integral)
         print("Transforming AO integrals to MO basis for (ia|jb) and (ij|ab) on the GPU...")

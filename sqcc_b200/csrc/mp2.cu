@@ -25,6 +25,16 @@ static int ensure_mp2work(sqcc_ctx *ctx, size_t bytes)
     if (ctx->d_mp2work) cudaFree(ctx->d_mp2work);
     ctx->d_mp2work = nullptr;
     ctx->mp2work_bytes = 0;
+    // the symmetrised pair matrix is npair^2 doubles (4.9 GB at N = 222, ~120 GB at N = 494): say so instead of failing
+    // inside cudaMalloc
+    size_t free_b = 0, total_b = 0;
+    SQCC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes > free_b) {
+        static char msg[192];
+        snprintf(msg, sizeof(msg), "AO->MO transform at N = %d needs %.1f GB of work space (pair matrix + intermediates), "
+                                   "%.1f GB free on the device", ctx->n, (double)bytes / 1e9, (double)free_b / 1e9);
+        SQCC_REQUIRE(false, msg);
+    }
     SQCC_CUDA(cudaMalloc(&ctx->d_mp2work, bytes));
     ctx->mp2work_bytes = bytes;
     return SQCC_OK;

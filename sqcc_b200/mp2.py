@@ -20,6 +20,9 @@ class Calculator:
         n_occ = int(scf.num_electrons / 2)
         engine = getattr(scf, "engine", None)
         if engine is None:   # an SCF object that did not come from sqcc_b200.hf_ksdft (e.g. loaded results)
+            if getattr(scf, "ao_electron_repulsion_integral", None) is None:
+                raise RuntimeError("the SCF object carries neither an engine nor the AO ERI tensor "
+                                   "(direct_ingest on several ranks keeps only shards): nothing to transform")
             engine = FockEngine()
             engine.attach_eri_full(scf.ao_electron_repulsion_integral)
         if engine.world != 1:
