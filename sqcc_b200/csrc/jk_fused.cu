@@ -29,6 +29,7 @@ struct JKParams {
     double fx_scale;            // deterministic mode: 2^shift of the fixed-point accumulators
     unsigned long long *trace;  // optional (tuning): per warp {first task start, last task end, tasks done} in ns
     int rotate;                 // each task starts its row-block list at a task-dependent offset (see jk_stream.cuh)
+    int overlap_prev;           // host side only: launch with programmatic stream serialization (see launch_stream)
 };
 
 // 16-byte read-only load that does not allocate in L1: with 227 KB of the SM's 256 KB carved out as shared memory the
@@ -280,7 +281,24 @@ static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
     int grid = ctx->sm_count;
     int max_useful = (p.ntasks + WARPS - 1) / WARPS;
     if (grid > max_useful) grid = max_useful > 0 ? max_useful : 1;
-    kern<<<grid, WARPS * 32, smem, ctx->stream>>>(p);
+    if (p.overlap_prev) {
+        // programmatic dependent launch: the CTAs of this kernel may start as soon as the previous kernel's CTAs have
+        // called griddepcontrol.launch_dependents and free their SM -- the narrow-piece pass and this kernel only add
+        // into the same accumulators, so the tail of the one overlaps the ramp-up of the other
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(WARPS * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SQCC_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    } else {
+        kern<<<grid, WARPS * 32, smem, ctx->stream>>>(p);
+    }
     ctx->launches++;
     ctx->trace_warps = grid * WARPS;
     SQCC_CUDA(cudaGetLastError());
@@ -376,6 +394,7 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
         const char *e = getenv("SQCC_JK_ROTATE");   // tuning knob: 0 = every task walks its row-block list from the start
         p.rotate = e ? atoi(e) : 1;
     }
+    p.overlap_prev = 0;
     p.fx_scale = 0.0;
     ctx->fx_scale = 0.0;
     if (ctx->jk_fixed) {
@@ -410,6 +429,10 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
                 SQCC_TRY((launch_stream<4, 1, false, 8, 2, false, false, true, 2>(ctx, pn)));
             else
                 SQCC_TRY((launch_stream<4, 1, true, 8, 2, false, false, true, 2>(ctx, pn)));
+        }
+        {
+            const char *e = getenv("SQCC_JK_PDL");   // tuning knob: 0 = plain stream order between the two passes
+            p.overlap_prev = (two_pass && sc_narrow.n_tasks > 0 && p.ntasks > 0 && (!e || atoi(e) != 0)) ? 1 : 0;
         }
         if (uhf_split)
             SQCC_TRY((launch_stream<4, 2, true, 8, 3, false, false, true, 1>(ctx, p)));

@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
     const uint64_t pol_stream = HINT ? l2_policy_evict_first() : 0, pol_keep = HINT ? l2_policy_evict_last() : 0;
     uint32_t stage_w = 0, stage_r = 0, phase_bits = 0;   // ring write / read positions and mbarrier parities, persist across tasks
 
+    // the narrow-piece pass lets the kernel launched behind it (same accumulators, no dependence on this one's results)
+    // take over every SM the moment this grid's CTA leaves it
+    if (KS) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (TMA) {
         if (lane == 0) {
 #pragma unroll
@@ -814,6 +817,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) jk_stream_kernel(const JKParams
         }
         __syncwarp();
     }
+    // launched with programmatic stream serialization behind the narrow-piece pass, this grid may run out of tasks while a
+    // CTA of that pass is still working: it must not complete (and release the kernel that reads the accumulators)
+    // before the pass has.  A no-op for a plain launch.
+    if (!KS) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 }  // namespace sqcc
