@@ -16,6 +16,7 @@ namespace sqcc {
 constexpr int GF_TM = 128;      // grid points per tile
 constexpr int GF_LD = 68;       // shared row stride (doubles)
 constexpr int GF_WARPS = 8;
+constexpr int GF_RHO_WARPS = 16;   // rho kernel: 128-point tiles, 8 rows per warp
 
 __device__ __forceinline__ void gf_cp16(void *dst, const void *src, bool on)
 {
@@ -30,7 +31,7 @@ __device__ __forceinline__ void gf_load_tile(double *At, const double *__restric
     const int half = n >> 1;
     const int chunks = TM * half;
     const int64_t g0 = t * TM;
-    for (int c = threadIdx.x; c < chunks; c += GF_WARPS * 32) {
+    for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
         const int r = c / half, cc = c - r * half;
         const bool on = g0 + r < G;
         gf_cp16(At + r * GF_LD + 2 * cc, phi + (on ? (g0 + r) * n + 2 * cc : 0), on);
@@ -39,7 +40,7 @@ __device__ __forceinline__ void gf_load_tile(double *At, const double *__restric
 }
 
 template <int NSPIN>
-__global__ void __launch_bounds__(GF_WARPS * 32, 1)
+__global__ void __launch_bounds__(GF_RHO_WARPS * 32, 1)
 grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w, const double *__restrict__ D, int64_t G,
                     int n, double c_pot, double c_en, double *__restrict__ rho_out, double *__restrict__ wv,
                     double *__restrict__ exc)
@@ -49,12 +50,12 @@ grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w
     double *At = Ds + NSPIN * 64 * GF_LD;           // [2][128][68]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // zero everything once (pad columns / rows must stay finite), then stage D
-    for (int e = tid; e < NSPIN * 64 * GF_LD + 2 * GF_TM * GF_LD; e += GF_WARPS * 32) gsm[e] = 0.0;
+    for (int e = tid; e < NSPIN * 64 * GF_LD + 2 * GF_TM * GF_LD; e += GF_RHO_WARPS * 32) gsm[e] = 0.0;
     __syncthreads();
     // rho_p = sum_mn phi_pm D_mn phi_pn = sum_{m <= n} phi_pm U_mn phi_pn with the upper-triangular U_mn = D_mn + D_nm
     // (m < n), U_mm = D_mm: the product T = phi U needs only the k-steps with k <= n of every column tile -- 72 of the 128
     // (k-step, column tile) pairs at N = 64 -- and is exact for any D, symmetric or not.
-    for (int e = tid; e < NSPIN * n * n; e += GF_WARPS * 32) {
+    for (int e = tid; e < NSPIN * n * n; e += GF_RHO_WARPS * 32) {
         const int s = e / (n * n), r = (e / n) % n, c = e % n;
         Ds[(s * 64 + r) * GF_LD + c] = r < c ? D[e] + D[(size_t)s * n * n + (size_t)c * n + r] : (r == c ? D[e] : 0.0);
     }
@@ -73,14 +74,13 @@ grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const double *A = At + buf * GF_TM * GF_LD + (warp * 16) * GF_LD;   // this warp's 16 rows
+        const double *A = At + buf * GF_TM * GF_LD + (warp * 8) * GF_LD;   // this warp's 8 rows (16 warps: four per scheduler
+                                                                            // hide the fragment loads and the epilogue)
 #pragma unroll
         for (int s = 0; s < NSPIN; ++s) {
-            double acc[2][8][2];
+            double acc[8][2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
             const double *B = Ds + s * 64 * GF_LD;
 #pragma unroll
             for (int jm = 0; jm < 8; ++jm) {       // k-steps 2 jm, 2 jm + 1 (rows 8 jm .. 8 jm + 7 of U) meet column tiles j >= jm
@@ -90,39 +90,35 @@ grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w
                     const int ks = 2 * jm + h;
                     if (ks >= ksteps) break;
                     const int kq = 4 * ks + (lane & 3);
-                    const double a0 = A[(lane >> 2) * GF_LD + kq], a1 = A[(8 + (lane >> 2)) * GF_LD + kq];
+                    const double a0 = A[(lane >> 2) * GF_LD + kq];
 #pragma unroll
                     for (int j = jm; j < 8; ++j) {
                         if (8 * j >= n) break;     // column tiles past the basis
                         const double b = B[kq * GF_LD + 8 * j + (lane >> 2)];
-                        dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, b);
-                        dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, b);
+                        dmma_m8n8k4(acc[j][0], acc[j][1], a0, b);
                     }
                 }
             }
-            // rho = rowdot(T, phi): lane holds T[row = lane/4 (+8)][col = 8j + 2(lane%4) + {0,1}]
-            double rsum[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int row = 8 * i + (lane >> 2);
+            // rho = rowdot(T, phi): lane holds T[row = lane/4][col = 8j + 2(lane%4) + {0,1}]
+            double rsum;
+            {
+                const int row = lane >> 2;
                 double part = 0.0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const double2 x = *reinterpret_cast<const double2 *>(A + row * GF_LD + 8 * j + 2 * (lane & 3));
-                    part = fma(acc[i][j][0], x.x, fma(acc[i][j][1], x.y, part));
+                    part = fma(acc[j][0], x.x, fma(acc[j][1], x.y, part));
                 }
                 part += __shfl_xor_sync(0xffffffffu, part, 1);
                 part += __shfl_xor_sync(0xffffffffu, part, 2);
-                rsum[i] = part;
+                rsum = part;
             }
-            // point functions: every lane of a quad holds both row sums; lane%4 == 0 finishes row lane/4, lane%4 == 1
-            // row 8 + lane/4 (16 lanes busy with ONE pow each instead of 8 lanes with two pows twice).
+            // point functions: every lane of a quad holds the row sum; lane%4 == 0 finishes row lane/4.
             // rho^(4/3) = rho * rho^(1/3): same NaN / zero behaviour as NumPy's pow, ~1 ulp from pow(rho, 4/3).
             {
-                const int i = lane & 3;
-                const int64_t g = t * GF_TM + warp * 16 + 8 * i + (lane >> 2);
-                if (i < 2 && g < G) {
-                    const double r = i == 0 ? rsum[0] : rsum[1];
+                const int64_t g = t * GF_TM + warp * 8 + (lane >> 2);
+                if ((lane & 3) == 0 && g < G) {
+                    const double r = rsum;
                     const double wg = w[g];
                     const double cb = pow(r, 1.0 / 3.0);   // pow like NumPy: NaN for rho < 0
                     if (rho_out) rho_out[s * G + g] = r;
@@ -134,14 +130,14 @@ grid_rho_lda_kernel(const double *__restrict__ phi, const double *__restrict__ w
         buf ^= 1;
     }
     // E_x: block reduction, one atomic per CTA
-    __shared__ double red[GF_WARPS];
+    __shared__ double red[GF_RHO_WARPS];
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) exc_part += __shfl_xor_sync(0xffffffffu, exc_part, o);
     if (lane == 0) red[warp] = exc_part;
     __syncthreads();
     if (tid == 0) {
         double sum = 0.0;
-        for (int i = 0; i < GF_WARPS; ++i) sum += red[i];
+        for (int i = 0; i < GF_RHO_WARPS; ++i) sum += red[i];
         atomicAdd(exc, c_en * sum);
     }
 }
@@ -253,7 +249,7 @@ static int launch_rho_lda(sqcc_ctx *ctx, const double *d_D, double c_pot, double
     SQCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (ctx->G + GF_TM - 1) / GF_TM;
     const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
-    kern<<<grid, GF_WARPS * 32, smem, ctx->stream>>>(ctx->d_phi, ctx->d_w, d_D, ctx->G, ctx->grid_n, c_pot, c_en, d_rho,
+    kern<<<grid, GF_RHO_WARPS * 32, smem, ctx->stream>>>(ctx->d_phi, ctx->d_w, d_D, ctx->G, ctx->grid_n, c_pot, c_en, d_rho,
                                                      d_wv, d_exc);
     ctx->launches++;
     SQCC_CUDA(cudaGetLastError());
