@@ -189,13 +189,13 @@ static int build_one_schedule(sqcc_ctx *ctx, JKSchedule &sc, int nb, int cw = JK
         }
     }
     const int nrb = (int)sc.h_rowblocks.size();
-    // group size: aim for >= ~16 tasks per resident warp, at least 4 and at most 32 row-blocks per task
+    // group size: aim for >= ~16 tasks per resident warp, at least 8 and at most 32 row-blocks per task
     int64_t warps = (int64_t)ctx->sm_count * 12;
     int nkr = (ctx->i_end + JK_KN - 1) / JK_KN;
     int nch = (ctx->i_end + cw - 1) / cw;
     int64_t cells = (int64_t)nrb * nkr * (nch + 1) / 2 / 2;  // rough count of (row-block, k-range, chunk) cells
     int group = (int)(cells / (warps * 16));
-    if (group < 4) group = 4;
+    if (group < 8) group = 8;   // (N = 222 / 264: 8-16 row-blocks per task are 1-2 % faster than 4, the guided tail keeps the balance)
     if (group > 32) group = 32;
     if (const char *e = getenv("SQCC_JK_GROUP")) {   // tuning knob: fixed row-blocks per task
         int g = atoi(e);
