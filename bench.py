@@ -283,15 +283,31 @@ def main():
     native_bytes, algo_bytes = eng.eri_bytes()
     peak, peak_src = peaks()
 
+    # ---- device-resident throughput (value).  Untimed warm-up: at least WARM_MIN builds -- the first ~20 builds after
+    # the ERI fill run 3-5 % slower (clock / power-state ramp, seen on every rank of the 8-GPU runs)
+    def warm_up(step):
+        """max(W, WARM_MIN) untimed steps, continued until WARM_SECONDS have passed (same count on every rank)."""
+        n_done, t_start = 0, time.perf_counter()
+        while True:
+            for _ in range(max(args.warmup, WARM_MIN)):
+                step()
+            n_done += max(args.warmup, WARM_MIN)
+            torch.cuda.synchronize()
+            go = torch.tensor([1.0 if time.perf_counter() - t_start < WARM_SECONDS else 0.0], device=eng.device)
+            if world > 1:
+                dist.all_reduce(go, op=dist.ReduceOp.MAX)
+            if go.item() == 0.0:
+                return n_done
+
     # ---- N > 1: the GPUs of a box sustain different clocks under their power caps; re-cut the shards from the measured
     # per-rank kernel times (the synthetic tensor is simply regenerated on the new cut) before anything is checked or timed
     shard_weights = None
     if world > 1 and not args.no_rebalance:
-        t_w = time.perf_counter()
-        while time.perf_counter() - t_w < 1.0:      # into the power-capped steady state first
-            for _ in range(10):
-                eng.jk_device(d_dev, True, out)
-            torch.cuda.synchronize()
+        # into the power-capped steady state first.  The number of builds must be the SAME on every rank (each build is a
+        # collective: the exchange kernel waits for all ranks) -- warm_up() agrees on it with an all-reduce; a loop on each
+        # rank's own wall clock lets two ranks disagree by one batch, and the rank that is ahead then sits in the next
+        # NCCL collective while the others spin in exchange kernels it never joins
+        warm_up(lambda: eng.jk_device(d_dev, True, out))
         shard_weights = eng.rebalance(steps=32, rounds=2)
         native_bytes, algo_bytes = eng.eri_bytes()
 
@@ -315,22 +331,6 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps
-
-    # ---- device-resident throughput (value).  Untimed warm-up: at least WARM_MIN builds -- the first ~20 builds after
-    # the ERI fill run 3-5 % slower (clock / power-state ramp, seen on every rank of the 8-GPU runs)
-    def warm_up(step):
-        """max(W, WARM_MIN) untimed steps, continued until WARM_SECONDS have passed (same count on every rank)."""
-        n_done, t_start = 0, time.perf_counter()
-        while True:
-            for _ in range(max(args.warmup, WARM_MIN)):
-                step()
-            n_done += max(args.warmup, WARM_MIN)
-            torch.cuda.synchronize()
-            go = torch.tensor([1.0 if time.perf_counter() - t_start < WARM_SECONDS else 0.0], device=eng.device)
-            if world > 1:
-                dist.all_reduce(go, op=dist.ReduceOp.MAX)
-            if go.item() == 0.0:
-                return n_done
 
     warm = warm_up(lambda: eng.jk_device(d_dev, True, out))
     barrier()
