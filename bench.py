@@ -110,6 +110,7 @@ class ClockSampler(threading.Thread):
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        time.sleep(0.005)   # first sample a few ms into the timed region (at 8 GPUs 20 steps last under 30 ms)
         while not self.stop_flag:
             try:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
@@ -120,7 +121,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.04)    # an NVML query can hold up kernel launches for a moment: sample sparsely
 
     def result(self):
         self.stop_flag = True
@@ -353,12 +354,13 @@ def main():
         timed(5)
     used_exchange = eng.exchange       # "nccl" if the peer mapping was refused and every rank fell back
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local) if rank == 0 else None   # (the JSON line reports rank 0's GPU)
+    if sampler:
+        sampler.start()
     l0 = eng.launch_count()
     eng.timings()                      # reset the timer ring: the kernel time below is the mean over the timed loop
     ms_per_step = timed(args.steps)
-    clocks = sampler.result()
+    clocks = sampler.result() if sampler else None
     launches = eng.launch_count() - l0
 
     # ---- dominant-kernel time: mean CUDA-event time of jk_stream_kernel over the launches of the timed loop above (at most
