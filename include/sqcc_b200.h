@@ -118,9 +118,6 @@ int sqcc_jk_set_variant(sqcc_ctx *ctx, int variant);
  * sqcc_eri_absmax(ctx, &v, 0) reads this shard's, sqcc_eri_absmax(ctx, &v, 1) sets the agreed one (max over ranks). */
 int sqcc_jk_set_deterministic(sqcc_ctx *ctx, int on);
 int sqcc_eri_absmax(sqcc_ctx *ctx, double *absmax, int set);
-/* Tuning aid: enable != 0 makes every warp of the pipelined kernel record {start ns, end ns, tasks done}; h_out (optional,
- * [max_warps][3]) receives the trace of the last launch.  Returns the number of warps written. */
-int sqcc_jk_trace(sqcc_ctx *ctx, int enable, uint64_t *h_out, int max_warps);
 
 /* ---- cross-rank exchange of the partial J/K over NVLink peer memory --------------------------
  * With a peer group attached, sqcc_jk_build / sqcc_jk_build_host return the FULL J/K on every rank: one kernel per

@@ -49,7 +49,6 @@ SIGNATURES = {
     "sqcc_comm_stamps": (c_int, [c_void_p, c_void_p]),
     "sqcc_jk_partial": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "sqcc_jk_reduce_local": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
-    "sqcc_jk_trace": (c_int, [c_void_p, c_int, c_void_p, c_int]),
     "sqcc_grid_attach": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int]),
     "sqcc_lda_vxc": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "sqcc_lda_vxc_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

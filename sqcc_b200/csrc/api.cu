@@ -164,7 +164,6 @@ int sqcc_ctx_destroy(sqcc_ctx *ctx)
     scf_free(ctx);
     comm_free(ctx);
     cudaFree(ctx->d_counter);
-    cudaFree(ctx->d_trace);
     cudaFree(ctx->d_io);
     cudaFree(ctx->d_gridwork);
     cudaFree(ctx->d_mp2work);
@@ -358,28 +357,6 @@ int sqcc_eri_absmax(sqcc_ctx *ctx, double *absmax, int set)
         *absmax = ctx->eri_absmax;
     }
     return SQCC_OK;
-}
-
-int sqcc_jk_trace(sqcc_ctx *ctx, int enable, uint64_t *h_out, int max_warps)
-{
-    SQCC_REQUIRE(ctx, "null ctx");
-    constexpr int CAP = 148 * 4 * 16;   // warps of the largest persistent grid
-    if (enable && !ctx->d_trace) {
-        SQCC_CUDA(cudaMalloc(&ctx->d_trace, sizeof(unsigned long long) * 3 * CAP));
-        SQCC_CUDA(cudaMemset(ctx->d_trace, 0, sizeof(unsigned long long) * 3 * CAP));
-    }
-    int nw = 0;
-    if (h_out && ctx->d_trace) {
-        nw = ctx->trace_warps < max_warps ? ctx->trace_warps : max_warps;
-        SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
-        SQCC_CUDA(cudaMemcpy(h_out, ctx->d_trace, sizeof(unsigned long long) * 3 * nw, cudaMemcpyDeviceToHost));
-    }
-    if (!enable && ctx->d_trace) {
-        SQCC_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_trace);
-        ctx->d_trace = nullptr;
-    }
-    return nw;
 }
 
 int sqcc_jk_build(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k, double *d_J, double *d_K)

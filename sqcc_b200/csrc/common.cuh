@@ -130,8 +130,6 @@ struct sqcc_ctx {
     double *d_acc = nullptr;     // [3][N][ldd]: J~, K~a, K~b (first part of comm.d_sym)
     sqcc::Comm comm;
     unsigned int *d_counter = nullptr;
-    unsigned long long *d_trace = nullptr;  // tuning: per-warp task trace of the last pipelined J/K launch (sqcc_jk_trace)
-    int trace_warps = 0;
     double *d_io = nullptr;      // device staging for *_host calls
     size_t io_bytes = 0;
     double *h_pin = nullptr;     // pinned staging

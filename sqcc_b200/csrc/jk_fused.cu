@@ -27,7 +27,6 @@ struct JKParams {
     int ntasks;
     unsigned int *counter;
     double fx_scale;            // deterministic mode: 2^shift of the fixed-point accumulators
-    unsigned long long *trace;  // optional (tuning): per warp {first task start, last task end, tasks done} in ns
     int rotate;                 // each task starts its row-block list at a task-dependent offset (see jk_stream.cuh)
     int overlap_prev;           // host side only: launch with programmatic stream serialization (see launch_stream)
 };
@@ -300,7 +299,6 @@ static int launch_stream(sqcc_ctx *ctx, const JKParams &p)
         kern<<<grid, WARPS * 32, smem, ctx->stream>>>(p);
     }
     ctx->launches++;
-    ctx->trace_warps = grid * WARPS;
     SQCC_CUDA(cudaGetLastError());
     return SQCC_OK;
 }
@@ -389,7 +387,6 @@ int jk_partial(sqcc_ctx *ctx, const double *d_D, int nspin, int want_k)
     p.rowblocks = sc.d_rowblocks;
     p.ntasks = sc.n_tasks;
     p.counter = ctx->d_counter;
-    p.trace = ctx->d_trace;
     {
         const char *e = getenv("SQCC_JK_ROTATE");   // tuning knob: 0 = every task walks its row-block list from the start
         p.rotate = e ? atoi(e) : 1;

@@ -3,23 +3,27 @@
 // A WARP is the unit of work.  A warp task is (16 sub-rows k) x (one 64-column chunk, two columns per lane) x (a list
 // of row-blocks: 4 rows i x NB rows j of one tile, NB = 4 for the single-density passes, 2 for the dual-density UHF
 // pass).  In the v2 layout the R = 4 NB rows of a row-block for one (k, chunk) are ONE contiguous piece and the 16
-// sub-rows of a task follow each other, so the ERI stream of a task is a single running pointer:
-//   * full pieces (64 columns): one elected lane issues ONE cp.async.bulk (TMA) per pipeline stage into the warp's
-//     shared-memory ring, completion on a per-stage mbarrier (UBLKCP in SASS);
-//   * the triangular edge (pieces of 16 / 32 / 48 columns, k - 64 c < 48): 16-byte cp.async per lane with immediate
-//     row offsets and the zero-fill form for the lanes past the piece, landing in the same [R][64] stage layout.
+// sub-rows of a task follow each other, so the ERI stream of a task is a single running pointer.  A slot of the warp's
+// shared-memory ring holds the piece of one loop iteration followed by the density tile row D2[k, chunk] of that sub-row:
+//   * full pieces (64 columns): one elected lane issues two cp.async.bulk (TMA) per slot -- piece and density row -- on
+//     one per-slot mbarrier (UBLKCP in SASS);
+//   * the triangular edge (pieces of 48 columns in this kernel, of 16 / 32 columns in the narrow-piece instantiation that
+//     runs two sub-rows per iteration on the half-warps): 16-byte cp.async per lane with immediate row offsets and the
+//     zero-fill form for the lanes past the piece, landing in the same slot layout.
 // Cells outside the canonical range are stored as 0.0, so the consumer is mask free and has no per-row address
 // arithmetic at all.
 //
 // Consumer, per sub-row: every lane holds D[j,l], D[i,l] (its two columns), the accumulators K~[i,l], K~[j,l], J~[i,j];
-// D[i,k], D[j,k] and D2[i,j] are warp-uniform (staged per row-block in shared memory, broadcast loads); J~[k,l] goes
-// to a warp-private slab that lives for the whole task.  K~[i,k], K~[j,k] need a sum over the lanes once per sub-row;
-// that reduction is SOFTWARE-PIPELINED over three iterations so that the loop body is one straight-line block in which
-// ptxas can place all the shuffles / shared-memory round trips in the issue slots the half-rate DFMAs leave free:
-//     iteration kk:   A  the 12 R DFMAs of sub-row kk                                    -> lane partials cd(kk)
-//                     B  xor-16 shuffle of cd(kk-1), 16 lanes store them (transposed)     -> s_red[(kk-1) & 1]
-//                     C  partials of kk-2: 4 loads, 3 adds, 2 shuffles, one store         -> s_kout[.][kk-2]
-// and the 16 x NV reduced values of a row-block leave with coalesced red.global.add.f64 after its sweep.
+// D[i,k], D[j,k] and D2[i,j] are warp-uniform (staged per row-block in shared memory by cp.async issued before the previous
+// row-block's epilogue, broadcast loads); J~[k,l] goes to a warp-private slab that lives for the whole task.  K~[i,k],
+// K~[j,k] need a sum over the lanes once per sub-row; that reduction is SOFTWARE-PIPELINED over three iterations so that
+// the loop body is one straight-line block in which ptxas can place all the shuffles / shared-memory round trips in the
+// issue slots the half-rate DFMAs leave free:
+//     iteration kk:   C  loads of the partials of kk-2 (before the warp barrier), 3 adds, 2 shuffles, one store -> s_kout[.][kk-2]
+//                     A  the 12 R DFMAs of sub-row kk                                                     -> lane partials cd(kk)
+//                     B  the half-warps swap halves of cd(kk-1) (one xor-16 shuffle per value pair) and store -> s_red
+// and the 16 x NV reduced values of a row-block leave with coalesced red.global.add.f64 after its sweep.  (The
+// dual-density pass has no registers for the third stage: it publishes cd(kk) itself, all 32 lane partials, unshuffled.)
 #pragma once
 
 namespace sqcc {
@@ -92,17 +96,6 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uin
                  "l"(src), "r"(bytes), "r"(bar), "l"(pol)
                  : "memory");
 }
-// 16-byte read-only load that asks L2 to keep the line (density tiles)
-__device__ __forceinline__ double2 ldg2_keep(const double *p, uint64_t pol)
-{
-    double2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 // xor-shuffle of a double without the volatile mov.b64 pack/unpack of the CUDA header
 __device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask)
 {
@@ -110,12 +103,6 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask)
     lo = __shfl_xor_sync(0xffffffffu, lo, lane_mask);
     hi = __shfl_xor_sync(0xffffffffu, hi, lane_mask);
     return __hiloint2double(hi, lo);
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
 }
 // Flushes to the global work matrices.  FIXED = false: red.global.add.f64 (result depends on the arrival order in the
 // last bits).  FIXED = true: the value is converted to 64-bit fixed point (scale 2^fx_shift, chosen by the prep kernel

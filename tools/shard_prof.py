@@ -29,18 +29,6 @@ for r in ranks:
     t = float(np.mean(ts))
     print(f"rank {r}/{world}: tiles [{eng.plan.t_begin},{eng.plan.t_end}) i [{eng.plan.i_begin},{eng.plan.i_end}) "
           f"native {nb / 1e9:.3f} GB algo {ab / 1e9:.3f} GB kernel {t:.4f} ms (min {min(ts):.4f})  {ab / t / 1e6:.0f} GB/s algo", flush=True)
-    if os.environ.get("SQCC_TRACE"):
-        import ctypes
-        eng.lib.sqcc_jk_trace(eng.ctx, 1, None, 0)
-        eng.jk_device(dd, True)
-        buf = np.zeros((148 * 16, 3), dtype=np.uint64)
-        nw = eng.lib.sqcc_jk_trace(eng.ctx, 0, buf.ctypes.data_as(ctypes.c_void_p), buf.shape[0])
-        tr = buf[:nw].astype(np.int64)
-        t0 = tr[:, 0].min()
-        end = np.sort(tr[:, 1] - t0) / 1e3
-        print(f"   trace: {nw} warps, kernel span {end[-1]:.1f} us; warp end percentiles (us) "
-              f"p0 {end[0]:.1f} p10 {end[nw // 10]:.1f} p50 {end[nw // 2]:.1f} p90 {end[nw * 9 // 10]:.1f} p100 {end[-1]:.1f}; "
-              f"start spread {(tr[:, 0].max() - t0) / 1e3:.1f} us; tasks/warp min {tr[:, 2].min()} max {tr[:, 2].max()} total {tr[:, 2].sum()}", flush=True)
     eng.close()
     del eng
     torch.cuda.empty_cache()
